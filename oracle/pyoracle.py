@@ -1,0 +1,164 @@
+"""ctypes front end of the CPU checkers in oracle/ -- TEST INFRASTRUCTURE ONLY.
+
+May be imported only by tests/, __graft_entry__.smoke() and bench.py's CPU legs
+(cpu_baseline, --impl reference).  The product package never imports this module.
+
+  Oracle("port")       -> oracle/libvdl2port.so          plain-C restatement
+  Oracle("ref")        -> oracle/_ref/libvdl2ref_O2.so   reference d8psk.c compiled in place, strict -O2
+  Oracle("ref_fast")   -> oracle/_ref/libvdl2ref_fast.so   same, project flags -Ofast (timing)
+  Oracle("ref_native") -> oracle/_ref/libvdl2ref_native.so same, -Ofast -march=native of the build host
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TAP_DUMPS, TAP_STEPS, TAP_SYNCS, TAP_SYMS, TAP_BLOCKS = 1, 2, 4, 8, 16
+TAP_ALL = 31
+
+STEP_DT = np.dtype([("dump", "<i8"), ("P", "<f4"), ("err", "<f4"), ("fr", "<f4"), ("pad", "<i4")])
+SYNC_DT = np.dtype([("dump", "<i8"), ("clk", "<i4"), ("df", "<f4"), ("ppm", "<f4"), ("P1", "<f4")])
+SYM_DT = np.dtype([("dump", "<i8"), ("D", "<f4"), ("P", "<f4"), ("gi", "<i4"), ("v", "<f4", (3,)),
+                   ("state_after", "<i4"), ("pad", "<i4")])
+BLOCK_DT = np.dtype([("sync_dump", "<i8"), ("end_dump", "<i8"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"),
+                     ("nbrow", "<i4"), ("nlbyte", "<i4"), ("data", "u1", (8, 255)), ("pad", "u1", (4,))])
+assert STEP_DT.itemsize == 24 and SYNC_DT.itemsize == 24 and SYM_DT.itemsize == 40 and BLOCK_DT.itemsize == 2080
+
+_PATHS = {
+    "port": os.path.join(HERE, "libvdl2port.so"),
+    "ref": os.path.join(HERE, "_ref", "libvdl2ref_O2.so"),
+    "ref_fast": os.path.join(HERE, "_ref", "libvdl2ref_fast.so"),
+    "ref_native": os.path.join(HERE, "_ref", "libvdl2ref_native.so"),
+}
+_LIBS: dict = {}
+
+
+def build(which: str = "all") -> None:
+    """Compile the checkers (port always; oracle/_ref only when /root/reference is mounted)."""
+    subprocess.run(["make", "-s", "-C", HERE, which], check=True)
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(_PATHS[kind])
+
+
+def load(kind: str):
+    if kind in _LIBS:
+        return _LIBS[kind]
+    path = _PATHS[kind]
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"oracle library {path} missing (run `make -C oracle`)")
+    lib = C.CDLL(path)
+    lib.orc_open.restype = C.c_void_p
+    lib.orc_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_uint32]
+    lib.orc_close.argtypes = [C.c_void_p]
+    for f in ("orc_feed_cf32", "orc_feed_f32real", "orc_feed_cs8", "orc_feed_cs16"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.orc_feed_cu8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float]
+    lib.orc_feed_rtl_block_quirk.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_tap.restype = C.c_void_p
+    lib.orc_tap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+    lib.orc_clear_taps.argtypes = [C.c_void_p]
+    lib.orc_ndump.restype = C.c_int64
+    lib.orc_ndump.argtypes = [C.c_void_p]
+    lib.orc_kind.restype = C.c_char_p
+    lib.orc_table.restype = C.POINTER(C.c_float)
+    lib.orc_table.argtypes = [C.c_int]
+    lib.orc_time_cu8.restype = C.c_double
+    lib.orc_time_cu8.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t, C.c_int]
+    _LIBS[kind] = lib
+    return lib
+
+
+def table(kind: str, which: int) -> np.ndarray:
+    """0 sync word, 1 interpolating filter (65), 2..4 soft demap tables (257)."""
+    n = {0: 17, 1: 65}.get(which, 257)
+    p = load(kind).orc_table(which)
+    return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+
+class Oracle:
+    """One channel of the CPU path: feed samples, read the taps."""
+
+    def __init__(self, kind: str = "port", chn: int = 0, Fr: int = 136_975_000, Fo: int = -50_000,
+                 fs: int = 2_000_000, sdrclk: int = 500, real_input: bool = False, taps: int = TAP_ALL):
+        self.lib = load(kind)
+        self.kind = kind
+        self.h = self.lib.orc_open(chn, Fr, Fo, fs, sdrclk, int(real_input), taps)
+
+    def close(self):
+        if self.h:
+            self.lib.orc_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def feed(self, iq: np.ndarray, fmt: str = "cu8"):
+        iq = np.ascontiguousarray(iq)
+        p = iq.ctypes.data_as(C.c_void_p)
+        if fmt == "cu8":
+            assert iq.dtype == np.uint8
+            self.lib.orc_feed_cu8(self.h, p, iq.size // 2, C.c_float(np.float32(127.37)))
+        elif fmt == "cs8":
+            assert iq.dtype == np.int8
+            self.lib.orc_feed_cs8(self.h, p, iq.size // 2)
+        elif fmt == "cs16":
+            assert iq.dtype == np.int16
+            self.lib.orc_feed_cs16(self.h, p, iq.size // 2)
+        elif fmt == "cf32":
+            assert iq.dtype == np.float32
+            self.lib.orc_feed_cf32(self.h, p, iq.size // 2)
+        elif fmt == "f32real":
+            assert iq.dtype == np.float32
+            self.lib.orc_feed_f32real(self.h, p, iq.size)
+        elif fmt == "rtl_quirk":
+            assert iq.dtype == np.uint8 and iq.size % 65536 == 0
+            for k in range(iq.size // 65536):
+                blk = iq[k * 65536:(k + 1) * 65536]
+                self.lib.orc_feed_rtl_block_quirk(self.h, blk.ctypes.data_as(C.c_void_p))
+        else:
+            raise ValueError(fmt)
+        return self
+
+    def _tap(self, which, dt):
+        n = C.c_size_t(0)
+        p = self.lib.orc_tap(self.h, which, C.byref(n))
+        if not p or n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (n.value * np.dtype(dt).itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    @property
+    def dumps(self):
+        return self._tap(TAP_DUMPS, np.dtype("<c8"))
+
+    @property
+    def steps(self):
+        return self._tap(TAP_STEPS, STEP_DT)
+
+    @property
+    def syncs(self):
+        return self._tap(TAP_SYNCS, SYNC_DT)
+
+    @property
+    def syms(self):
+        return self._tap(TAP_SYMS, SYM_DT)
+
+    @property
+    def blocks(self):
+        return self._tap(TAP_BLOCKS, BLOCK_DT)
+
+    @property
+    def ndump(self):
+        return int(self.lib.orc_ndump(self.h))
+
+
+def time_cu8(kind: str, iq: np.ndarray, reps: int, Fr=136_975_000, Fo=-50_000, fs=2_000_000, sdrclk=500) -> float:
+    """Seconds for `reps` passes of one private channel over `iq` (taps off); GIL released."""
+    lib = load(kind)
+    iq = np.ascontiguousarray(iq)
+    return float(lib.orc_time_cu8(Fr, Fo, fs, sdrclk, iq.ctypes.data_as(C.c_void_p), iq.size // 2, reps))
