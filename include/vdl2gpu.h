@@ -1,0 +1,154 @@
+/*
+ * vdl2gpu.h -- C ABI of the B200-native VDL Mode 2 front-end DSP path.
+ *
+ * Drop-in scope: exactly the per-IQ-sample hot path of TLeconte/vdlm2dec
+ *   sample conversion            rtl.c:285-292 / air.c:206-208
+ *   NCO mix + integrate-and-dump d8psk.c:343-382 (rcv_thread)
+ *   interpolating filter, sync fit, timing, D8PSK slicer   d8psk.c:219-333
+ *   soft demap, descrambler, header decode, de-interleave  d8psk.c:54-217, viterbi.c:37-96
+ * up to the hand-off of a completed msgblk_t (decodeVdlm2(), vdlm2.c:189).
+ * Everything downstream (rs.c, crc.c, out*.c) stays host code of the reference.
+ *
+ * The reference has no plugin API: the seam is the object d8psk.o (vdlm2.h:113-114,128).
+ * Two layers are exported by libvdl2gpu.so:
+ *   1. the batch API below (plain pointers and sizes), which is what a cgo/ctypes/FFI
+ *      binding or the reference's C code calls;
+ *   2. libvdl2shim.so / d8psk_gpu.o, which re-exports the reference
+ *      symbols rcv_thread / initD8psk / reversebits on top of layer 1.
+ *
+ * Conventions follow the reference (rtl.c:200-204): int return, 0 = OK, non-zero = failure
+ * with a message retrievable through vdl2_last_error() (and printed on stderr).
+ * There is NO CPU fallback: every entry point fails if no sm_100 device is usable.
+ */
+#ifndef VDL2GPU_H
+#define VDL2GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDL2_ABI_VERSION 1
+
+/* input sample formats; CU8 is what rtl.c receives (rtl.c:287-289: x - 127.37f),
+   CF32 is the already converted Cbuff of the reference (vdlm2.h:89),
+   F32REAL is the Airspy real-sample mode (air.c:123,206-208). */
+enum vdl2_format {
+	VDL2_FMT_CU8 = 0,	/* unsigned 8-bit I,Q; value - 127.37f */
+	VDL2_FMT_CS8 = 1,	/* signed 8-bit I,Q */
+	VDL2_FMT_CS16 = 2,	/* signed 16-bit I,Q */
+	VDL2_FMT_CF32 = 3,	/* float32 I,Q */
+	VDL2_FMT_F32REAL = 4	/* float32 real samples */
+};
+
+/* optional observation points; they cost HBM writes, keep off in production */
+#define VDL2_TAP_DUMPS 1u	/* T1: the 84 ksps decimated stream */
+#define VDL2_TAP_STEPS 2u	/* T2: P, err, fr of every idle (WSYNC) step */
+#define VDL2_TAP_SYNCS 4u	/* T3: trigger events */
+#define VDL2_TAP_SYMS  8u	/* T4/T5: per-symbol differential phase, Gray index, 3 soft bits */
+
+/* mirrors thread_param_t (vdlm2.h:49-52) */
+typedef struct {
+	int chn;		/* channel number reported in blocks */
+	int Fr;			/* channel frequency, Hz */
+	int Fo;			/* offset from the tuner centre, Hz (multiple of 25 kHz, d8psk.c:348-357) */
+} vdl2_chan_param_t;
+
+typedef struct {
+	unsigned fs;		/* SDRINRATE (rtl.c:36 / air.c:37) */
+	unsigned sdrclk;	/* SDRCLK    (rtl.c:37 / air.c:38,138) */
+	int format;		/* enum vdl2_format */
+	int nch;		/* channels */
+	int ch_per_stream;	/* channels demodulated from each input stream (1..8); nch % ch_per_stream == 0 */
+	int device;		/* CUDA device ordinal */
+	unsigned taps;		/* VDL2_TAP_* mask */
+	size_t max_samples;	/* largest nsamples (per stream) of one vdl2_process_* call */
+	int max_blocks;		/* capacity of the completed-block queue between drains (0 = default) */
+} vdl2_config_t;
+
+/* completed block = the fields of msgblk_t the demodulator owns (vdlm2.h:39-47):
+   ppm (d8psk.c:302), nbrow/nlbyte (d8psk.c:94-95), data[r][0..254] (d8psk.c:127,176).
+   tv is wall-clock in the reference (d8psk.c:295); here the trigger position is given
+   in 84 kHz dump units and in input samples so the caller can synthesise it. */
+typedef struct {
+	int64_t sync_dump;	/* index (since create) of the decimated sample that triggered */
+	int64_t end_dump;	/* index of the decimated sample that completed the block */
+	int32_t chn;
+	int32_t Fr;
+	float ppm;
+	int32_t nbrow;
+	int32_t nlbyte;
+	uint8_t data[8][255];
+	uint8_t pad[4];
+} vdl2_block_t;			/* 2080 bytes */
+
+typedef struct {
+	int64_t dump;
+	float P, err, fr;
+	int32_t pad;
+} vdl2_step_t;
+
+typedef struct {
+	int64_t dump;
+	int32_t clk;
+	float df, ppm, P1;
+} vdl2_sync_t;
+
+typedef struct {
+	int64_t dump;
+	float D, P;
+	int32_t gi;
+	float v[3];
+	int32_t state_after;
+	int32_t pad;
+} vdl2_sym_t;
+
+typedef struct {
+	uint64_t kernel_launches;	/* front-end kernel launches since create */
+	uint64_t samples_in;		/* per-stream samples accepted */
+	uint64_t samples_done;		/* per-stream samples demodulated (whole 1 ms rows) */
+	uint64_t blocks_out;		/* blocks completed */
+	uint64_t blocks_dropped;	/* blocks lost to a full queue */
+	float last_kernel_ms;		/* device time of the last launch (CUDA events) */
+	int n_sm;
+	int grid;			/* persistent warps launched */
+	int smem_bytes;			/* dynamic shared memory per warp-CTA */
+} vdl2_stats_t;
+
+typedef struct vdl2gpu vdl2gpu_t;
+
+int vdl2_abi_version(void);
+const char *vdl2_last_error(const vdl2gpu_t * h);	/* h may be NULL: error of the last failed create */
+
+int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, vdl2gpu_t ** out);
+int vdl2_destroy(vdl2gpu_t * h);
+
+/* Host input: iq holds nstreams = nch/ch_per_stream streams, stream s at iq + s*pitch_bytes,
+   nsamples samples each (interleaved I,Q in cfg.format).  Copies H2D, demodulates every
+   complete 1 ms row (the sub-millisecond tail is kept for the next call, like the
+   reference carries clk/nf/no across blocks, d8psk.c:343-347) and returns when done. */
+int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes);
+
+/* Device input, same layout, already resident in HBM.  Zero-copy when no tail is pending
+   and nsamples is a whole number of rows; asynchronous on the handle's stream. */
+int vdl2_process_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes);
+int vdl2_sync(vdl2gpu_t * h);
+
+/* completed blocks since the last drain, oldest trigger first (the msgblk_t hand-off) */
+int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out);
+
+/* taps (only what cfg.taps enabled); each read returns and clears the channel's records */
+int vdl2_read_dumps(vdl2gpu_t * h, int ch, float *iq_out, size_t max, size_t *n_out);
+int vdl2_read_steps(vdl2gpu_t * h, int ch, vdl2_step_t * out, size_t max, size_t *n_out);
+int vdl2_read_syncs(vdl2gpu_t * h, int ch, vdl2_sync_t * out, size_t max, size_t *n_out);
+int vdl2_read_syms(vdl2gpu_t * h, int ch, vdl2_sym_t * out, size_t max, size_t *n_out);
+
+int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
+/* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */
+void *vdl2_cuda_stream(vdl2gpu_t * h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

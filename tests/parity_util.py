@@ -1,0 +1,87 @@
+"""Shared helpers for the parity tests: run the CPU oracle and the CUDA path on the same
+seeded input and compare the tap points T1..T6."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle.pyoracle import Oracle
+from vdlm2dec_b200 import synth
+
+D_TOL = 1e-5  # rad, absolute: the north_star's soft-symbol tolerance (DESIGN.md "numerics")
+
+
+def make_channels(nch, nsamples, seed=1, fs=2_000_000, fmt="cu8", period=60000, **kw):
+    """nch independent streams; Fo cycles over the legal 25 kHz raster (|Fo| >= 50 kHz)."""
+    fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+    specs, iqs = [], []
+    for c in range(nch):
+        spec = synth.standard_channel(seed=seed * 1000 + c, nsamples=nsamples, Fo=fos[c % len(fos)], fs=fs,
+                                      period=period, **kw)
+        specs.append(spec)
+        iqs.append(synth.render_channel(spec, nsamples, fs=fs, fmt=fmt))
+    return specs, np.stack(iqs)
+
+
+def run_oracle(iq_row, Fo, fmt="cu8", kind="port", fs=2_000_000, sdrclk=500, chn=0, Fr=136_975_000):
+    o = Oracle(kind, chn=chn, Fr=Fr, Fo=Fo, fs=fs, sdrclk=sdrclk)
+    o.feed(iq_row, fmt)
+    return o
+
+
+def wrap_diff(a, b):
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    return np.minimum(d, np.abs(2 * np.pi - d))
+
+
+def compare_channel(o: Oracle, g_blocks, g_syncs=None, g_syms=None, g_dumps=None, g_steps=None, ndump_limit=None):
+    """Returns a dict of findings; raises AssertionError on a parity failure."""
+    rep = {}
+    ob = o.blocks
+    if ndump_limit is not None:
+        ob = ob[ob["end_dump"] < ndump_limit]
+    rep["blocks"] = (len(ob), len(g_blocks))
+    assert len(ob) == len(g_blocks), f"block count oracle {len(ob)} vs gpu {len(g_blocks)}"
+    for i, (a, b) in enumerate(zip(ob, g_blocks)):
+        for f in ("sync_dump", "end_dump", "nbrow", "nlbyte"):
+            assert a[f] == b[f], f"block {i} field {f}: oracle {a[f]} gpu {b[f]}"
+        assert np.array_equal(a["data"], b["data"]), f"block {i}: data bytes differ ({(a['data'] != b['data']).sum()})"
+        assert abs(float(a["ppm"]) - float(b["ppm"])) <= 1e-4 * max(1.0, abs(float(a["ppm"]))), f"block {i} ppm"
+    if g_dumps is not None:
+        od = o.dumps[:len(g_dumps)]
+        scale = np.sqrt(np.mean(np.abs(od) ** 2)) + 1e-30
+        err = np.abs(od - g_dumps).max() / scale
+        rep["dumps_relerr"] = float(err)
+        assert err < 1e-5, f"decimated stream deviates {err:.3e} of rms"
+    if g_syncs is not None:
+        os_ = o.syncs
+        if ndump_limit is not None:
+            os_ = os_[os_["dump"] < ndump_limit]
+        assert len(os_) == len(g_syncs), f"sync count oracle {len(os_)} gpu {len(g_syncs)}"
+        assert np.array_equal(os_["dump"], g_syncs["dump"]), "sync positions differ"
+        assert np.array_equal(os_["clk"], g_syncs["clk"]), "sync timing (clk) differs"
+        rep["sync_df_err"] = float(np.abs(os_["df"] - g_syncs["df"]).max()) if len(os_) else 0.0
+        assert rep["sync_df_err"] < D_TOL
+    if g_syms is not None:
+        osy = o.syms
+        if ndump_limit is not None:
+            osy = osy[osy["dump"] < ndump_limit]
+        assert len(osy) == len(g_syms), f"symbol count oracle {len(osy)} gpu {len(g_syms)}"
+        if len(osy):
+            assert np.array_equal(osy["dump"], g_syms["dump"]), "symbol positions differ"
+            rep["sym_D_err"] = float(wrap_diff(osy["D"], g_syms["D"]).max())
+            rep["gi_flips"] = int((osy["gi"] != g_syms["gi"]).sum())
+            assert rep["sym_D_err"] < D_TOL, f"soft symbol deviates {rep['sym_D_err']:.3e} rad"
+            assert rep["gi_flips"] == 0, f"{rep['gi_flips']} Gray index flips"
+            assert np.array_equal(osy["v"].view(np.uint32), g_syms["v"].view(np.uint32)), "soft bits differ"
+    if g_steps is not None:
+        ost = o.steps
+        if ndump_limit is not None:
+            ost = ost[ost["dump"] < ndump_limit]
+        assert len(ost) == len(g_steps), f"step count oracle {len(ost)} gpu {len(g_steps)}"
+        if len(ost):
+            assert np.array_equal(ost["dump"], g_steps["dump"]), "step positions differ"
+            rep["step_P_err"] = float(wrap_diff(ost["P"], g_steps["P"]).max())
+            m = ost["err"] >= 0
+            rel = np.abs(ost["err"][m] - g_steps["err"][m]) / np.maximum(1.0, np.abs(ost["err"][m]))
+            rep["step_err_rel"] = float(rel.max()) if m.any() else 0.0
+    return rep

@@ -1,0 +1,187 @@
+"""Python mirror of the C ABI in include/vdl2gpu.h (ctypes, no torch types in the boundary).
+
+The reference is a C program without a plugin API; its seam for this path is the object
+d8psk.o (vdlm2.h:113-114).  This module is the thin host-side mirror used by the parity
+tests and the bench: the names follow the reference (thread_param_t -> ChanParam with
+chn/Fr/Fo, msgblk_t -> BLOCK_DT with ppm/nbrow/nlbyte/data).
+
+There is no CPU fallback: importing works without a GPU (so the symbol checks can run on
+a CPU box), but constructing a Vdl2Gpu needs an sm_100 device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvdl2gpu.so")
+
+FORMATS = {"cu8": 0, "cs8": 1, "cs16": 2, "cf32": 3, "f32real": 4}
+FMT_DTYPE = {"cu8": np.uint8, "cs8": np.int8, "cs16": np.int16, "cf32": np.float32, "f32real": np.float32}
+FMT_BYTES = {"cu8": 2, "cs8": 2, "cs16": 4, "cf32": 8, "f32real": 4}
+TAP_DUMPS, TAP_STEPS, TAP_SYNCS, TAP_SYMS = 1, 2, 4, 8
+
+STEP_DT = np.dtype([("dump", "<i8"), ("P", "<f4"), ("err", "<f4"), ("fr", "<f4"), ("pad", "<i4")])
+SYNC_DT = np.dtype([("dump", "<i8"), ("clk", "<i4"), ("df", "<f4"), ("ppm", "<f4"), ("P1", "<f4")])
+SYM_DT = np.dtype([("dump", "<i8"), ("D", "<f4"), ("P", "<f4"), ("gi", "<i4"), ("v", "<f4", (3,)),
+                   ("state_after", "<i4"), ("pad", "<i4")])
+BLOCK_DT = np.dtype([("sync_dump", "<i8"), ("end_dump", "<i8"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"),
+                     ("nbrow", "<i4"), ("nlbyte", "<i4"), ("data", "u1", (8, 255)), ("pad", "u1", (4,))])
+assert BLOCK_DT.itemsize == 2080
+
+
+class ChanParam(C.Structure):  # thread_param_t, vdlm2.h:49-52
+    _fields_ = [("chn", C.c_int), ("Fr", C.c_int), ("Fo", C.c_int)]
+
+
+class Config(C.Structure):
+    _fields_ = [("fs", C.c_uint), ("sdrclk", C.c_uint), ("format", C.c_int), ("nch", C.c_int),
+                ("ch_per_stream", C.c_int), ("device", C.c_int), ("taps", C.c_uint),
+                ("max_samples", C.c_size_t), ("max_blocks", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("samples_in", C.c_uint64), ("samples_done", C.c_uint64),
+                ("blocks_out", C.c_uint64), ("blocks_dropped", C.c_uint64), ("last_kernel_ms", C.c_float),
+                ("n_sm", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int)]
+
+
+EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
+           "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
+           "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libvdl2gpu.so; raises (loudly) when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m vdlm2dec_b200.build` "
+                           "(there is no CPU fallback for the VDL2 front end)")
+    lib = C.CDLL(LIB_PATH)
+    lib.vdl2_abi_version.restype = C.c_int
+    lib.vdl2_last_error.restype = C.c_char_p
+    lib.vdl2_last_error.argtypes = [C.c_void_p]
+    lib.vdl2_create.argtypes = [C.POINTER(Config), C.POINTER(ChanParam), C.POINTER(C.c_void_p)]
+    lib.vdl2_destroy.argtypes = [C.c_void_p]
+    lib.vdl2_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_sync.argtypes = [C.c_void_p]
+    lib.vdl2_drain_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    for f in ("vdl2_read_dumps", "vdl2_read_steps", "vdl2_read_syncs", "vdl2_read_syms"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.vdl2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.vdl2_cuda_stream.restype = C.c_void_p
+    lib.vdl2_cuda_stream.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class Vdl2Error(RuntimeError):
+    pass
+
+
+class Vdl2Gpu:
+    """A set of channels demodulated on one B200: feed IQ, drain completed blocks.
+
+    chans: sequence of (chn, Fr, Fo) -- the reference's thread_param_t per channel.
+    Channels c*ch_per_stream .. (c+1)*ch_per_stream-1 are demodulated from input stream c.
+    """
+
+    def __init__(self, chans: Sequence[tuple[int, int, int]], fs: int = 2_000_000, sdrclk: int = 500,
+                 fmt: str = "cu8", ch_per_stream: int = 1, device: int = 0, taps: int = 0,
+                 max_samples: int = 1 << 22, max_blocks: int = 0):
+        self.lib = load_library()
+        self.fmt = fmt
+        self.nch = len(chans)
+        self.ch_per_stream = ch_per_stream
+        self.nstreams = self.nch // ch_per_stream
+        self.bps = FMT_BYTES[fmt]
+        self.max_samples = max_samples
+        arr = (ChanParam * self.nch)(*[ChanParam(*c) for c in chans])
+        cfg = Config(fs, sdrclk, FORMATS[fmt], self.nch, ch_per_stream, device, taps, max_samples, max_blocks)
+        self.h = C.c_void_p()
+        if self.lib.vdl2_create(C.byref(cfg), arr, C.byref(self.h)):
+            raise Vdl2Error(self.lib.vdl2_last_error(None).decode())
+        self._cap_blocks = max_blocks if max_blocks > 0 else max(4096, self.nch * 8)
+
+    def _check(self, rc):
+        if rc:
+            raise Vdl2Error(self.lib.vdl2_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vdl2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- input
+    def process(self, iq: np.ndarray):
+        """Host buffer: [nstreams, nsamples*k] (or flat for one stream), dtype of the format."""
+        iq = np.ascontiguousarray(iq, dtype=FMT_DTYPE[self.fmt])
+        if iq.ndim == 1:
+            iq = iq.reshape(1, -1)
+        assert iq.shape[0] == self.nstreams, (iq.shape, self.nstreams)
+        row_bytes = iq.shape[1] * iq.itemsize
+        nsamples = row_bytes // self.bps
+        self._check(self.lib.vdl2_process_host(self.h, iq.ctypes.data_as(C.c_void_p), nsamples, row_bytes))
+        return self
+
+    def process_ptr(self, host_ptr: int, nsamples: int, pitch_bytes: int):
+        self._check(self.lib.vdl2_process_host(self.h, C.c_void_p(host_ptr), nsamples, pitch_bytes))
+
+    def process_device(self, dev_ptr: int, nsamples: int, pitch_bytes: int):
+        """Device-resident input (e.g. a torch tensor's data_ptr()); asynchronous, see sync()."""
+        self._check(self.lib.vdl2_process_device(self.h, C.c_void_p(dev_ptr), nsamples, pitch_bytes))
+
+    def sync(self):
+        self._check(self.lib.vdl2_sync(self.h))
+
+    # ---- output
+    def drain_blocks(self) -> np.ndarray:
+        out = np.zeros(self._cap_blocks, dtype=BLOCK_DT)
+        n = C.c_int(0)
+        self._check(self.lib.vdl2_drain_blocks(self.h, out.ctypes.data_as(C.c_void_p), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def _read(self, fn, ch, dt, cap):
+        out = np.zeros(cap, dtype=dt)
+        n = C.c_size_t(0)
+        self._check(fn(self.h, ch, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def _rows_cap(self):
+        return self.max_samples // 1000 * 84 // (2_000_000 // 1000) + 4096
+
+    def read_dumps(self, ch: int) -> np.ndarray:
+        cap = (self.max_samples // 20 + 4096)
+        return self._read(self.lib.vdl2_read_dumps, ch, np.dtype("<c8"), cap)
+
+    def read_steps(self, ch: int) -> np.ndarray:
+        return self._read(self.lib.vdl2_read_steps, ch, STEP_DT, self.max_samples // 40 + 4096)
+
+    def read_syncs(self, ch: int) -> np.ndarray:
+        return self._read(self.lib.vdl2_read_syncs, ch, SYNC_DT, self.max_samples // 1000 + 4096)
+
+    def read_syms(self, ch: int) -> np.ndarray:
+        return self._read(self.lib.vdl2_read_syms, ch, SYM_DT, self.max_samples // 160 + 4096)
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self.lib.vdl2_get_stats(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.lib.vdl2_cuda_stream(self.h) or 0)

@@ -1,0 +1,96 @@
+/*
+ * vdl2_common.h -- structures shared by the host side of libvdl2gpu and the sm_100a kernel.
+ * Vocabulary follows the reference: a "dump" is one 84 ksps integrate-and-dump output
+ * (d8psk.c:374-381), a "step" is one idle-mode sync evaluation (d8psk.c:248-313),
+ * a "row" is 1 ms of input (the joint period of the 21/SDRCLK dump clock and the 25 kHz
+ * NCO table): fs/1000 samples, always 84 dumps.
+ */
+#ifndef VDL2_COMMON_H
+#define VDL2_COMMON_H
+#include <stdint.h>
+
+#define VDL2_DUMPS_PER_ROW 84
+#define VDL2_ROWS_PER_TILE 32	/* one row per lane */
+#define VDL2_TILE_DUMPS (VDL2_DUMPS_PER_ROW * VDL2_ROWS_PER_TILE)	/* 2688 */
+#define VDL2_HIST 16		/* dumps of history in front of a tile (MBUFLEN-1) */
+#define VDL2_PHHIST 64		/* idle-mode phases of history ((NBPH-1)*D8DWN) */
+#define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
+#define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
+
+#define VDL2_TAP_DUMPS_BIT 1u
+#define VDL2_TAP_STEPS_BIT 2u
+#define VDL2_TAP_SYNCS_BIT 4u
+#define VDL2_TAP_SYMS_BIT 8u
+
+enum { VDL2_ST_WSYNC = 0, VDL2_ST_GETHEAD = 1, VDL2_ST_GETDATA = 2 };	/* GETFEC is folded into GETDATA */
+
+/* per-channel demodulator state kept in HBM between tiles and calls: the GPU analogue of
+   channel_t (vdlm2.h:56-79) plus the rcv_thread locals that survive a block (d8psk.c:343-347) */
+struct Vdl2ChanState {
+	float hist_re[VDL2_HIST], hist_im[VDL2_HIST];	/* last 16 dumps (Inbuff ring, oldest first) */
+	float ph[VDL2_PHHIST];	/* last 64 idle-mode phases, ph[63] newest (Ph ring in logical order) */
+	float hv[28];		/* descrambled header soft bits collected so far */
+	float perr, p2err, pfr, df, P1, ppm;
+	int32_t clk, state;
+	int32_t symidx;		/* symbols sliced since the trigger */
+	int32_t nbrow, nlbyte;	/* header values (d8psk.c:94-95) */
+	int32_t bytes_done;	/* data+FEC bytes stored so far */
+	int32_t bitacc, nbitacc;	/* partial byte, LSB first */
+	int64_t sync_dump;
+	int32_t chn, Fr;
+	uint32_t n_steps, n_syncs, n_syms, n_dumps;	/* tap record counts */
+	int32_t pad[6];
+};
+
+/* constant tables of the kernel */
+struct Vdl2Tables {
+	float mflt[68];		/* interpolating low-pass taps, 65 used (d8psk.h:28-45) */
+	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
+	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
+	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
+	unsigned char sched[VDL2_MAX_CHUNKS];	/* mixer: last sample of a dump inside each 16-byte chunk, or samples-per-chunk */
+	float scale[VDL2_DUMPS_PER_ROW];	/* mixer: 1/nf of each dump of a row */
+	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
+};
+
+/* completed-block record: identical layout to vdl2_block_t (include/vdl2gpu.h) */
+struct Vdl2BlockRec {
+	int64_t sync_dump, end_dump;
+	int32_t chn, Fr;
+	float ppm;
+	int32_t nbrow, nlbyte;
+	uint8_t data[8 * 255];
+	uint8_t pad[4];
+};
+
+struct Vdl2StepRec { int64_t dump; float P, err, fr; int32_t pad; };
+struct Vdl2SyncRec { int64_t dump; int32_t clk; float df, ppm, P1; };
+struct Vdl2SymRec  { int64_t dump; float D, P; int32_t gi; float v[3]; int32_t state_after; int32_t pad; };
+
+/* kernel arguments (the TMA descriptor travels separately as a __grid_constant__) */
+struct Vdl2KParams {
+	int nch, ch_per_stream;
+	int ntiles;		/* tiles of 32 rows in this launch */
+	int nrows;		/* rows in this launch (last tile may be short) */
+	int chunks_per_row;	/* row bytes / 16 */
+	int nbox;		/* 128-byte column boxes per row */
+	int nco_pairs;		/* NCO table length in sample pairs */
+	int64_t dump_base;	/* global dump index of row 0 of this launch */
+	Vdl2ChanState *state;
+	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
+	unsigned *ticket;	/* work counter */
+	int *progress;		/* [nch]: tiles completed in this launch */
+	uint8_t *curblk;	/* [nch][2048] block under construction */
+	Vdl2BlockRec *outq;
+	unsigned *outq_count;
+	unsigned outq_cap;
+	unsigned *dropped;
+	unsigned taps;
+	float2 *tap_dumps;	/* [nch][cap_dumps] */
+	Vdl2StepRec *tap_steps;	/* [nch][cap_steps] */
+	Vdl2SyncRec *tap_syncs;	/* [nch][cap_syncs] */
+	Vdl2SymRec *tap_syms;	/* [nch][cap_syms] */
+	unsigned cap_dumps, cap_steps, cap_syncs, cap_syms;
+};
+
+#endif

@@ -1,0 +1,566 @@
+/*
+ * vdl2_demod.cuh -- phase 2 of the front-end kernel: the D8PSK demodulator state machine,
+ * one warp per channel, LANES OVER TIME.
+ *
+ * Input: the channel's decimated 84 ksps stream for one tile (<= 2688 dumps) in shared
+ * memory, preceded by the 16 dumps of history.  The reference runs this as a strictly
+ * sequential per-sample state machine (d8psk.c:232-333); here it is restated so that a
+ * warp evaluates 32 consecutive idle-mode steps (or 32 consecutive symbols) at once:
+ *
+ *   idle (WSYNC, d8psk.c:241-313): a step happens every 2nd dump with a constant tap phase
+ *     r = clk mod 4; step n is a pure function of the 17-dump window (-> phase P_n) and of
+ *     the 17 phases P_{n-64}, P_{n-60}, .. P_n.  Each lane runs
+ *     the complete 17-point line fit for its own step in the reference's operation order;
+ *     the trigger `perr < 4 && err > perr` (d8psk.c:292) is evaluated with the neighbour
+ *     lane's err through shuffles and the first trigger is found with ballot/ffs; steps
+ *     after it are discarded (the reference would not have run them in idle mode).
+ *   burst (GETHEAD/GETDATA/GETFEC, d8psk.c:314-332, :67-209): a symbol every 8th dump, tap
+ *     phase constant; lanes slice 32 symbols at once, soft-demap and descramble them; the
+ *     25-bit header goes through a lane-per-state restatement of the 32-state max-product
+ *     trellis (viterbi.c:37-96, per channel instead of the reference's global arrays);
+ *     payload bits are packed to bytes with ballots and scattered to data[row][col] through
+ *     the closed form of the reference's column-major de-interleave (d8psk.c:117-206).
+ *
+ * The file is written against the small `vw::` warp layer so that tests/emul can compile
+ * the SAME source for the host with a fibre-based 32-lane warp emulator and check it
+ * against the oracle without a GPU (test infrastructure; the product builds only the
+ * CUDA variant).
+ */
+#ifndef VDL2_DEMOD_CUH
+#define VDL2_DEMOD_CUH
+#include "vdl2_common.h"
+#include "vdl2_tables.h"
+
+#ifdef __CUDACC__
+#define VQ __device__ __forceinline__
+#define VDL2_CONST __constant__
+namespace vw {
+VQ int lane() { return threadIdx.x & 31; }
+VQ void sync() { __syncwarp(); }
+template <class T> VQ T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class T> VQ T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+VQ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+VQ unsigned atomic_inc(unsigned *p) { return atomicAdd(p, 1u); }
+VQ void fence() { __threadfence(); }
+VQ int ffs(unsigned m) { return __ffs(m); }
+VQ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+VQ float atan2(float y, float x) { return atan2f(y, x); }
+VQ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
+VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
+VQ float fmul(float a, float b) { return __fmul_rn(a, b); }
+template <class T> VQ T ldcg(const T * p) { return __ldcg(p); }
+}
+#else
+#include "vdl2_emul.h"		/* tests/emul: host definitions of VQ, VDL2_CONST and vw:: */
+#endif
+
+/* constant tables (struct Vdl2Tables, vdl2_common.h), filled by the host at create time.
+   This header is included by exactly one translation unit per build, so it defines it. */
+VDL2_CONST Vdl2Tables c_tab;
+
+namespace vdl2 {
+
+#define VDL2_PI_F 3.14159274101257324f	/* smallest float above M_PI: (double)x > M_PI  <=>  x >= VDL2_PI_F */
+#define VDL2_2PI_HI 6.28318548202514648f
+#define VDL2_2PI_LO (-1.74845553146951715e-07f)
+#define VDL2_PI_D 3.14159265358979323846
+
+/* parity-check columns of the (25,20) header code (viterbi.c:29-35), from the constant table */
+VQ int hcol(int n)
+{
+	return c_tab.hcol[n];
+}
+
+VQ unsigned revbits(unsigned in, int n)
+{				/* d8psk.c:39-52 */
+	unsigned out = 0;
+	for (int i = 0; i < n; i++) {
+		out = (out << 1) | (in & 1);
+		in >>= 1;
+	}
+	return out;
+}
+
+/* Interpolating low-pass + phase (filteredphase, d8psk.c:219-230) for the dump at tile index d:
+   window sd[d .. d+16] (sd carries 16 dumps of history in front), oldest first, taps
+   mflt[clk], mflt[clk+4], ... < 65.  General tap phase; used at the trigger. */
+VQ float filt_phase_any(const float2 * sd, int d, int clk)
+{
+	float sr = 0.f, si = 0.f;
+	int j = 0;
+	for (int i = clk; i < VDL2_MFLTLEN; i += 4, j++) {
+		const float m = c_tab.mflt[i];
+		const float2 x = sd[d + j];
+		sr = vw::fma(x.x, m, sr);
+		si = vw::fma(x.y, m, si);
+	}
+	return vw::atan2(si, sr);
+}
+
+/* same, steady state: r in 0..3 -> 17 taps (tap 64 is the implicit zero when r = 0, and
+   r + 64 > 64 reads the zero padding of the table for r > 0) */
+VQ float filt_phase17(const float2 * sd, int d, const float *m)
+{
+	float sr = 0.f, si = 0.f;
+#pragma unroll
+	for (int j = 0; j < 17; j++) {
+		const float2 x = sd[d + j];
+		sr = vw::fma(x.x, m[j], sr);
+		si = vw::fma(x.y, m[j], si);
+	}
+	return vw::atan2(si, sr);
+}
+
+/* 17-point least-squares line through the unwrapped (phase - unique word) sequence
+   (d8psk.c:259-289).  ph[4*l] is the phase of symbol l.  Returns residual and slope. */
+VQ void sync_fit(const float *ph, float &err_out, float &fr_out)
+{
+	float Pr[VDL2_NBPH];
+	float kf = 0.f, Pv, M;
+	M = Pv = Pr[0] = ph[0] - c_tab.sync[0];
+#pragma unroll
+	for (int l = 1; l < VDL2_NBPH; l++) {
+		const float Pc = ph[4 * l] - c_tab.sync[l];
+		const float Pd = Pc - Pv;
+		Pv = Pc;
+		/* the reference keeps Pu = (float)(Pu -+ 2*M_PI); kf counts the net turns and
+		   Pu is rebuilt as the correctly rounded kf*2pi (differs from the sequentially
+		   rounded value by <= 1 ulp, see DESIGN.md "numerics") */
+		kf += (Pd >= VDL2_PI_F) ? -1.f : ((Pd <= -VDL2_PI_F) ? 1.f : 0.f);
+		const float Pu = vw::fma(kf, VDL2_2PI_HI, kf * VDL2_2PI_LO);
+		Pr[l] = Pc + Pu;
+		M += Pr[l];
+	}
+	M = vw::fdiv(M, 17.f);
+	float fr = 0.f;
+#pragma unroll
+	for (int l = 0; l < VDL2_NBPH; l++) {
+		Pr[l] -= M;
+		fr = vw::fma(Pr[l], (float)(l - 8), fr);
+	}
+	fr = vw::fdiv(fr, 408.f);
+	float err = 0.f;
+#pragma unroll
+	for (int l = 0; l < VDL2_NBPH; l++) {
+		const float e = vw::fma(-(float)(l - 8), fr, Pr[l]);
+		err = vw::fma(e, e, err);
+	}
+	err_out = err;
+	fr_out = fr;
+}
+
+/* burst geometry from the header (d8psk.c:94-95, :139-162, :188-197) */
+struct BurstGeom {
+	int nbrow, nlbyte;	/* data phase */
+	int frow, flast;	/* FEC phase: rows, bytes of the short last row (0 = all rows full) */
+	int nd, nf;		/* bytes in each phase */
+	int nsym;		/* symbols from the trigger to the end of the burst */
+};
+
+VQ BurstGeom burst_geom(int nbrow, int nlbyte)
+{
+	BurstGeom g;
+	g.nbrow = nbrow;
+	g.nlbyte = nlbyte;
+	g.nd = nlbyte ? nlbyte * nbrow + (249 - nlbyte) * (nbrow - 1) : 249 * nbrow;
+	if (nlbyte <= 2) {
+		g.frow = nbrow - 1;
+		g.flast = 0;
+	} else {
+		g.frow = nbrow;
+		g.flast = nlbyte <= 30 ? 2 : (nlbyte <= 67 ? 4 : 0);
+	}
+	g.nf = g.flast ? g.flast * g.frow + (6 - g.flast) * (g.frow - 1) : 6 * g.frow;
+	g.nsym = (25 + 8 * (g.nd + g.nf) + 2) / 3;
+	return g;
+}
+
+/* byte number B of the burst payload -> offset in data[8][255] */
+VQ int byte_slot(const BurstGeom & g, int B)
+{
+	int r, c;
+	if (B < g.nd) {
+		const int full = g.nlbyte * g.nbrow;
+		if (g.nlbyte == 0 || B < full) {
+			c = B / g.nbrow;
+			r = B - c * g.nbrow;
+		} else {
+			const int b2 = B - full, w = g.nbrow - 1;
+			const int q = b2 / w;
+			c = g.nlbyte + q;
+			r = b2 - q * w;
+		}
+	} else {
+		const int b1 = B - g.nd;
+		const int full = g.flast * g.frow;
+		if (g.flast == 0 || b1 < full) {
+			c = b1 / g.frow;
+			r = b1 - c * g.frow;
+		} else {
+			const int b2 = b1 - full, w = g.frow - 1;
+			const int q = b2 / w;
+			c = g.flast + q;
+			r = b2 - q * w;
+		}
+		c += 249;
+	}
+	return r * 255 + c;
+}
+
+/* 25-bit header through the 32-state max-product trellis, lane = state (viterbi.c:37-96).
+   The update order of the reference (ascending source state, '1' branch before '0') decides
+   ties; it is reproduced by ordering the two candidates of a target state by source index. */
+VQ unsigned header_decode(const float *hv)
+{
+	const int s = vw::lane();
+	double pb = (s == 0) ? 1.0 : 0.0;
+	unsigned hist = 0;
+	for (int n = 0; n < 25; n++) {
+		const float V = hv[n];
+		const int src1 = s ^ hcol(n);
+		const double p1 = vw::shfl(pb, src1);
+		const double c1 = p1 * (double)V;
+		const double c0 = pb * (1.0 - (double)V);
+		const bool v1 = (p1 != 0.0), v0 = (pb != 0.0);
+		double nw = 0.0;
+		unsigned bit = 0;
+		if (src1 < s) {
+			if (v1 && c1 > nw) { nw = c1; bit = 1; }
+			if (v0 && c0 > nw) { nw = c0; bit = 0; }
+		} else {
+			if (v0 && c0 > nw) { nw = c0; bit = 0; }
+			if (v1 && c1 > nw) { nw = c1; bit = 1; }
+		}
+		pb = nw;
+		hist |= bit << n;
+	}
+	unsigned bits = 0, b = 1;
+	int st = 0;
+	for (int n = 25; n > 0; n--) {
+		const unsigned h = vw::shfl(hist, st);
+		const unsigned bit = (h >> (n - 1)) & 1u;
+		if (bit) {
+			bits |= b;
+			st ^= hcol(n - 1);
+		}
+		b <<= 1;
+	}
+	return bits;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * demod_tile: consume dumps [0, nd) of one tile.
+ *   sd   : shared, float2[16 + nd], sd[16 + i] = dump i, sd[0..15] = history
+ *   phb  : shared, float[96]; phb[0..63] = the 64 previous idle-mode phases (oldest first)
+ *   hv   : shared, float[28]; header soft bits collected so far
+ *   st   : the channel's state in HBM (read at entry, written back at exit by the caller
+ *          through the ChanRegs copy below)
+ * ------------------------------------------------------------------------------------- */
+struct ChanRegs {		/* warp-uniform working copy of the scalar state */
+	float perr, p2err, pfr, df, P1, ppm;
+	int clk, state, symidx, nbrow, nlbyte, bytes_done, bitacc, nbitacc;
+	long long sync_dump;
+	unsigned n_steps, n_syncs, n_syms;
+};
+
+VQ void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long end_dump, int chn, int Fr)
+{
+	const int lane = vw::lane();
+	unsigned slot = 0;
+	if (lane == 0)
+		slot = vw::atomic_inc(kp.outq_count);
+	slot = vw::shfl(slot, 0);
+	unsigned *cur = (unsigned *)(kp.curblk + (size_t) ch * 2048);
+	if (slot < kp.outq_cap) {
+		Vdl2BlockRec *rec = kp.outq + slot;
+		unsigned *dst = (unsigned *)rec->data;	/* 2040 bytes = 510 words, 8-byte aligned */
+		for (int i = lane; i < 510; i += 32)
+			dst[i] = vw::ldcg(cur + i);
+		if (lane == 0) {
+			rec->sync_dump = R.sync_dump;
+			rec->end_dump = end_dump;
+			rec->chn = chn;
+			rec->Fr = Fr;
+			rec->ppm = R.ppm;
+			rec->nbrow = R.nbrow;
+			rec->nlbyte = R.nlbyte;
+		}
+	} else if (lane == 0) {
+		vw::atomic_inc(kp.dropped);
+	}
+	vw::sync();
+	for (int i = lane; i < 512; i += 32)	/* fresh zeroed block (calloc in vdlm2.c:201) */
+		cur[i] = 0;
+	vw::sync();
+}
+
+VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, float *phb, float *hv,
+		   int nd, long long dump_base)
+{
+	const int lane = vw::lane();
+	int pos = 0;
+	unsigned char *curblk = kp.curblk + (size_t) ch * 2048;
+
+	while (pos < nd) {
+		if (R.state == VDL2_ST_WSYNC) {
+			/* ---- idle mode: up to 32 steps at dumps p0, p0+2, ... (d8psk.c:248-313) ---- */
+			if (R.clk >= 8)
+				R.clk &= 7;	/* unreachable for finite input (clk < 8 whenever the burst clock was sane) */
+			const int c4 = R.clk >= 4;
+			const int p0 = pos + (c4 ? 0 : 1);
+			const int r = c4 ? R.clk - 4 : R.clk;
+			if (p0 >= nd) {
+				R.clk += 4 * (nd - pos);
+				pos = nd;
+				break;
+			}
+			const int nsteps = ((nd - 1 - p0) >> 1) + 1;
+			const int nb = nsteps < 32 ? nsteps : 32;
+			float m[17];
+#pragma unroll
+			for (int j = 0; j < 17; j++)
+				m[j] = c_tab.mflt[r + 4 * j];	/* r + 64 <= 67: zero padded */
+			const int d = p0 + 2 * lane;
+			float Pn = 0.f;
+			if (lane < nb)
+				Pn = filt_phase17(sd, d, m);
+			phb[VDL2_PHHIST + lane] = Pn;
+			vw::sync();
+			float err, fr;
+			sync_fit(phb + lane, err, fr);
+			const float e1 = vw::shfl_up(err, 1), e2 = vw::shfl_up(err, 2), f1 = vw::shfl_up(fr, 1);
+			const float perr_l = lane >= 1 ? e1 : R.perr;
+			const float p2err_l = lane >= 2 ? e2 : (lane == 1 ? R.perr : R.p2err);
+			const float pfr_l = lane >= 1 ? f1 : R.pfr;
+			const bool trig = (lane < nb) && (perr_l < 4.0f) && (err > perr_l);
+			const unsigned tm = vw::ballot(trig);
+			const int K = tm ? vw::ffs(tm) : nb;	/* steps committed, trigger step included */
+
+			if ((kp.taps & VDL2_TAP_STEPS_BIT) && lane < K) {
+				const unsigned idx = R.n_steps + lane;
+				if (idx < kp.cap_steps) {
+					Vdl2StepRec s;
+					s.dump = dump_base + d;
+					s.P = Pn;
+					const bool tl = tm && lane == K - 1;
+					s.err = tl ? -1.0f : err;
+					s.fr = tl ? pfr_l : fr;
+					s.pad = 0;
+					kp.tap_steps[(size_t) ch * kp.cap_steps + idx] = s;
+				}
+			}
+			R.n_steps += (kp.taps & VDL2_TAP_STEPS_BIT) ? K : 0;
+
+			/* commit K phases: slide the 64-entry history */
+			const float k0 = phb[lane + K], k1 = phb[lane + 32 + K];
+			vw::sync();
+			phb[lane] = k0;
+			phb[lane + 32] = k1;
+			vw::sync();
+
+			if (!tm) {
+				const float eL = vw::shfl(err, K - 1), fL = vw::shfl(fr, K - 1);
+				const float eP = vw::shfl(err, K >= 2 ? K - 2 : 0);
+				R.p2err = K >= 2 ? eP : R.perr;
+				R.perr = eL;
+				R.pfr = fL;
+				pos = p0 + 2 * (K - 1) + 1;
+				R.clk = r;
+			} else {
+				/* trigger (d8psk.c:292-308) at step T = K-1 */
+				const int T = K - 1;
+				const float eT = vw::shfl(err, T), pT = vw::shfl(perr_l, T);
+				const float p2T = vw::shfl(p2err_l, T), fT = vw::shfl(pfr_l, T);
+				const int dT = p0 + 2 * T;
+				R.state = VDL2_ST_GETHEAD;
+				R.symidx = 0;
+				R.df = fT;
+				R.ppm = (float)((double)vw::fmul(10500.0f, R.df) / (2.0 * VDL2_PI_D * (double)Fr) * 1e6);
+				const float num = vw::fmul(4.0f, vw::fadd(vw::fsub(p2T, vw::fmul(4.0f, pT)), vw::fmul(3.0f, eT)));
+				const float den = vw::fadd(vw::fsub(p2T, vw::fmul(2.0f, pT)), eT);
+				const float of = vw::fdiv(num, den);
+				int nclk = (int)roundf(of);
+				nclk = nclk < 0 ? 0 : (nclk > 64 ? 64 : nclk);	/* of is in [4,12] for finite input */
+				R.clk = nclk;
+				R.P1 = filt_phase_any(sd, dT, nclk);
+				R.perr = R.p2err = 500.f;
+				R.sync_dump = dump_base + dT;
+				if ((kp.taps & VDL2_TAP_SYNCS_BIT)) {
+					if (lane == 0 && R.n_syncs < kp.cap_syncs) {
+						Vdl2SyncRec s;
+						s.dump = R.sync_dump;
+						s.clk = nclk;
+						s.df = R.df;
+						s.ppm = R.ppm;
+						s.P1 = R.P1;
+						kp.tap_syncs[(size_t) ch * kp.cap_syncs + R.n_syncs] = s;
+					}
+					R.n_syncs++;
+				}
+				pos = dT + 1;
+			}
+		} else {
+			/* ---- burst: up to 32 symbols at dumps ds0, ds0+8, ... (d8psk.c:314-332) ---- */
+			const int c = R.clk;
+			const int k0 = (c >= 28) ? 1 : ((35 - c) >> 2);
+			const int r = c + 4 * k0 - 32;
+			const int ds0 = pos + k0 - 1;
+			if (ds0 >= nd) {
+				R.clk += 4 * (nd - pos);
+				pos = nd;
+				break;
+			}
+			const bool head = (R.state == VDL2_ST_GETHEAD);
+			BurstGeom g;
+			if (!head)
+				g = burst_geom(R.nbrow, R.nlbyte);
+			int nb = ((nd - 1 - ds0) >> 3) + 1;
+			const int remain = head ? 9 - R.symidx : g.nsym - R.symidx;
+			nb = nb < remain ? nb : remain;
+			nb = nb < 32 ? nb : 32;
+			if (r >= 4)
+				nb = 1;	/* irregular clock (only after a non-finite timing estimate) */
+			const int d = ds0 + 8 * lane;
+			float Pn = 0.f;
+			if (lane < nb)
+				Pn = filt_phase_any(sd, d, r);
+			float Pp = vw::shfl_up(Pn, 1);
+			if (lane == 0)
+				Pp = R.P1;
+			float D = vw::fsub(vw::fsub(Pn, Pp), R.df);
+			if (D >= VDL2_PI_F)
+				D = (float)((double)D - 2.0 * VDL2_PI_D);
+			if (D <= -VDL2_PI_F)
+				D = (float)((double)D + 2.0 * VDL2_PI_D);
+			int gi = (int)roundf((float)(128.0 * (double)D / VDL2_PI_D + 128.0));	/* d8psk.c:213 */
+			gi = gi < 0 ? 0 : (gi > 256 ? 256 : gi);
+			if (lane >= nb)
+				gi = 128;
+			const int si = R.symidx + lane;
+			float v[3], V[3];
+			unsigned hard = 0;
+#pragma unroll
+			for (int q = 0; q < 3; q++) {
+				v[q] = c_tab.soft[q][gi];
+				const int b = 3 * si + q;
+				const unsigned sb = (c_tab.scr[(b >> 5) & (VDL2_SCR_WORDS - 1)] >> (b & 31)) & 1u;
+				V[q] = sb ? vw::fsub(1.0f, v[q]) : v[q];	/* descrambler, d8psk.c:54-65 */
+				hard |= (V[q] > 0.5f ? 1u : 0u) << q;
+			}
+			const float Plast = vw::shfl(Pn, nb - 1);
+
+			if ((kp.taps & VDL2_TAP_SYMS_BIT) && lane < nb) {
+				const unsigned idx = R.n_syms + lane;
+				if (idx < kp.cap_syms) {
+					Vdl2SymRec s;
+					s.dump = dump_base + d;
+					s.D = D;
+					s.P = Pn;
+					s.gi = gi;
+					s.v[0] = v[0];
+					s.v[1] = v[1];
+					s.v[2] = v[2];
+					s.state_after = 0;
+					s.pad = 0;
+					kp.tap_syms[(size_t) ch * kp.cap_syms + idx] = s;
+				}
+			}
+			R.n_syms += (kp.taps & VDL2_TAP_SYMS_BIT) ? nb : 0;
+
+			const int dl = ds0 + 8 * (nb - 1);	/* dump of the last symbol of the batch */
+			if (head) {
+				/* header bits 0..26 (d8psk.c:77-116): first three forced to 0 */
+				if (lane < nb) {
+#pragma unroll
+					for (int q = 0; q < 3; q++) {
+						const int b = 3 * si + q;
+						hv[b] = (b < 3) ? 0.f : V[q];
+					}
+				}
+				vw::sync();
+				R.symidx += nb;
+				R.P1 = Plast;
+				R.clk = r;
+				pos = dl + 1;
+				if (R.symidx == 9) {
+					const unsigned w = header_decode(hv) >> 5;
+					const unsigned len = revbits(w, 17);
+					R.nbrow = (int)(len / 1992u) + 1;
+					R.nlbyte = (int)((len % 1992u + 7u) / 8u);
+					if (len < 96u || R.nbrow > 8) {
+						R.state = VDL2_ST_WSYNC;	/* d8psk.c:97-107 */
+					} else {
+						R.state = VDL2_ST_GETDATA;
+						R.bytes_done = 0;
+						/* bits 25 and 26 are already payload (d8psk.c:117-123) */
+						R.bitacc = (hv[25] > 0.5f ? 1 : 0) | (hv[26] > 0.5f ? 2 : 0);
+						R.nbitacc = 2;
+					}
+				}
+			} else {
+				/* payload: pack 3 bits per lane into bytes, LSB first (d8psk.c:117-206) */
+				const unsigned m0 = vw::ballot(hard & 1u), m1 = vw::ballot(hard & 2u), m2 = vw::ballot(hard & 4u);
+				const int nbits = R.nbitacc + 3 * nb;
+				const int total = g.nd + g.nf;
+				int nbytes = nbits >> 3;
+				if (R.bytes_done + nbytes > total)
+					nbytes = total - R.bytes_done;
+				if (lane < nbytes) {
+					unsigned byte = 0;
+#pragma unroll
+					for (int i = 0; i < 8; i++) {
+						const int p = 8 * lane + i;
+						unsigned bit;
+						if (p < R.nbitacc) {
+							bit = ((unsigned)R.bitacc >> p) & 1u;
+						} else {
+							const int p2 = p - R.nbitacc;
+							const int j = (p2 * 43691) >> 17;	/* p2 / 3 */
+							const int q = p2 - 3 * j;
+							const unsigned mm = q == 0 ? m0 : (q == 1 ? m1 : m2);
+							bit = (mm >> j) & 1u;
+						}
+						byte |= bit << i;
+					}
+					curblk[byte_slot(g, R.bytes_done + lane)] = (unsigned char)byte;
+				}
+				/* bits left over for the next batch */
+				int left = nbits - 8 * nbytes;
+				unsigned acc = 0;
+				if (left > 7)
+					left = 0;	/* only at the end of the burst: discarded (d8psk.c:203) */
+				for (int i = 0; i < left; i++) {
+					const int p = 8 * nbytes + i;
+					unsigned bit;
+					if (p < R.nbitacc) {
+						bit = ((unsigned)R.bitacc >> p) & 1u;
+					} else {
+						const int p2 = p - R.nbitacc;
+						const int j = p2 / 3;
+						const int q = p2 - 3 * j;
+						const unsigned mm = q == 0 ? m0 : (q == 1 ? m1 : m2);
+						bit = (mm >> j) & 1u;
+					}
+					acc |= bit << i;
+				}
+				R.bitacc = (int)acc;
+				R.nbitacc = left;
+				R.bytes_done += nbytes;
+				R.symidx += nb;
+				R.P1 = Plast;
+				R.clk = r;
+				pos = dl + 1;
+				if (R.bytes_done >= total) {
+					vw::fence();
+					vw::sync();
+					emit_block(kp, ch, R, dump_base + dl, chn, Fr);	/* decodeVdlm2 hand-off, d8psk.c:201 */
+					R.state = VDL2_ST_WSYNC;
+				}
+			}
+		}
+	}
+}
+
+}				/* namespace vdl2 */
+#endif

@@ -1,0 +1,576 @@
+/*
+ * vdl2_host.cu -- host side of libvdl2gpu.so: the C ABI of include/vdl2gpu.h.
+ *
+ * Owns the device buffers (per-channel state, NCO tables, block queue, tap logs, the input
+ * staging ring), builds the TMA descriptor for every launch and launches the fused
+ * front-end kernel.  No demodulation happens on the host; if CUDA is unavailable every
+ * entry point fails (there is deliberately no CPU fallback).
+ *
+ * Host-side arithmetic that must equal the reference's:
+ *   NCO table   d8psk.c:353-357   wf[n] = cexpf(-n * Fo' * I), Fo' rounded to float,
+ *               evaluated here with the same glibc cexpf so the table is bit-identical;
+ *   dump clock  d8psk.c:374-381   clk += 21; dump when clk >= SDRCLK  -> schedule table.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "vdl2_kernel.h"
+#include "vdl2_tables.h"
+
+static_assert(sizeof(Vdl2BlockRec) == sizeof(vdl2_block_t), "block record layout");
+static_assert(sizeof(Vdl2StepRec) == sizeof(vdl2_step_t), "step record layout");
+static_assert(sizeof(Vdl2SyncRec) == sizeof(vdl2_sync_t), "sync record layout");
+static_assert(sizeof(Vdl2SymRec) == sizeof(vdl2_sym_t), "sym record layout");
+
+static thread_local std::string g_create_error;
+
+struct vdl2gpu {
+	vdl2_config_t cfg;
+	int nstreams;
+	int bytes_per_sample;	/* per IQ sample (or per real sample) */
+	int row_samples, row_bytes, chunks_per_row, nbox, spc;
+	int nco_entries;
+	int smem, grid, n_sm, ctas_per_sm;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	bool ev_valid;
+	/* device */
+	Vdl2ChanState *d_state;
+	float4 *d_wtab;
+	unsigned *d_ticket;
+	int *d_progress;
+	uint8_t *d_curblk;
+	Vdl2BlockRec *d_outq;
+	unsigned *d_outq_count, *d_dropped;
+	unsigned outq_cap;
+	float2 *d_tap_dumps;
+	Vdl2StepRec *d_tap_steps;
+	Vdl2SyncRec *d_tap_syncs;
+	Vdl2SymRec *d_tap_syms;
+	unsigned cap_dumps, cap_steps, cap_syncs, cap_syms;
+	uint8_t *d_stage;	/* [nstreams][stage_pitch]: carry + new samples */
+	size_t stage_pitch;
+	size_t carry;		/* samples pending at the head of each staging stream */
+	int64_t rows_done;
+	vdl2_stats_t st;
+	std::string err;
+	void *encode_fn;
+};
+
+static int fail(vdl2gpu * h, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	fprintf(stderr, "vdl2gpu: %s\n", buf);	/* reference convention: message on stderr, non-zero return */
+	if (h)
+		h->err = buf;
+	else
+		g_create_error = buf;
+	return 1;
+}
+
+#define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+extern "C" int vdl2_abi_version(void)
+{
+	return VDL2_ABI_VERSION;
+}
+
+extern "C" const char *vdl2_last_error(const vdl2gpu_t * h)
+{
+	return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+static int fmt_bytes(int fmt)
+{
+	switch (fmt) {
+	case VDL2_FMT_CU8: case VDL2_FMT_CS8: return 2;
+	case VDL2_FMT_CS16: return 4;
+	case VDL2_FMT_CF32: return 8;
+	case VDL2_FMT_F32REAL: return 4;
+	}
+	return 0;
+}
+
+static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
+{
+	memset(&t, 0, sizeof t);
+	float mf[VDL2_MFLTLEN], sw[VDL2_NBPH];
+	static float soft[3][257];
+	vdl2_make_mflt(mf);
+	vdl2_make_sync(sw);
+	vdl2_make_softmap(soft);
+	memcpy(t.mflt, mf, sizeof mf);
+	memcpy(t.sync, sw, sizeof sw);
+	for (int b = 0; b < 3; b++)
+		memcpy(t.soft[b], soft[b], sizeof soft[b]);
+	/* descrambler sequence (d8psk.c:54-65), seed 0x4D4B (d8psk.c:299) */
+	unsigned s = 0x4D4B;
+	for (int i = 0; i < VDL2_SCR_WORDS * 32; i++) {
+		unsigned b = (s ^ (s >> 14)) & 1u;
+		s = (s << 1) | b;
+		t.scr[i >> 5] |= b << (i & 31);
+	}
+	static const unsigned char hc[25] = { 0x06, 0x07, 0x09, 0x0a, 0x0b, 0x0c, 0x0e, 0x0f, 0x11, 0x13, 0x15, 0x16, 0x18,
+		0x19, 0x1a, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f, 0x10, 0x08, 0x04, 0x02, 0x01
+	};			/* viterbi.c:29-35 */
+	memcpy(t.hcol, hc, sizeof hc);
+	/* dump schedule of one row (d8psk.c:374-381) */
+	int clk = 0, nf = 0, k = 0;
+	for (int c = 0; c < h->chunks_per_row; c++)
+		t.sched[c] = (unsigned char)h->spc;
+	for (int n = 0; n < h->row_samples; n++) {
+		nf++;
+		clk += 21;
+		if (clk >= (int)h->cfg.sdrclk) {
+			clk %= (int)h->cfg.sdrclk;
+			t.sched[n / h->spc] = (unsigned char)(n % h->spc);
+			if (k < VDL2_DUMPS_PER_ROW)
+				t.scale[k] = 1.0f / (float)nf;
+			k++;
+			nf = 0;
+		}
+	}
+}
+
+extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, vdl2gpu_t ** out)
+{
+	if (!cfg || !chans || !out)
+		return fail(NULL, "vdl2_create: null argument");
+	*out = NULL;
+	if (cfg->nch <= 0 || cfg->ch_per_stream <= 0 || cfg->nch % cfg->ch_per_stream)
+		return fail(NULL, "vdl2_create: nch=%d must be a positive multiple of ch_per_stream=%d", cfg->nch, cfg->ch_per_stream);
+	if (cfg->format != VDL2_FMT_CU8 && cfg->format != VDL2_FMT_CS8 && cfg->format != VDL2_FMT_CF32)
+		return fail(NULL, "vdl2_create: format %d not built into this library (cu8, cs8, cf32 are)", cfg->format);
+	if (cfg->fs % 1000 || cfg->fs % VDL2_STEPRATE || cfg->sdrclk == 0 || (cfg->fs / 1000 * 21) % cfg->sdrclk)
+		return fail(NULL, "vdl2_create: fs=%u / sdrclk=%u do not give a 1 ms joint period", cfg->fs, cfg->sdrclk);
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(NULL, "vdl2_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+	if (cfg->device < 0 || cfg->device >= ndev)
+		return fail(NULL, "vdl2_create: device %d out of range (%d present)", cfg->device, ndev);
+	CK(NULL, cudaSetDevice(cfg->device));
+	cudaDeviceProp prop;
+	CK(NULL, cudaGetDeviceProperties(&prop, cfg->device));
+	if (prop.major < 10)
+		return fail(NULL, "vdl2_create: device %d is sm_%d%d; the kernels are built for sm_100a only", cfg->device, prop.major,
+			    prop.minor);
+
+	vdl2gpu *h = new vdl2gpu();
+	h->cfg = *cfg;
+	h->nstreams = cfg->nch / cfg->ch_per_stream;
+	h->bytes_per_sample = fmt_bytes(cfg->format);
+	h->row_samples = cfg->fs / 1000;
+	h->row_bytes = h->row_samples * h->bytes_per_sample;
+	h->spc = 16 / h->bytes_per_sample;
+	h->ev_valid = false;
+	h->carry = 0;
+	h->rows_done = 0;
+	memset(&h->st, 0, sizeof h->st);
+	if (h->row_bytes % 16 || h->row_bytes / 16 > VDL2_MAX_CHUNKS) {
+		delete h;
+		return fail(NULL, "vdl2_create: row of %d bytes is not a whole number of 16-byte chunks", h->row_bytes);
+	}
+	h->chunks_per_row = h->row_bytes / 16;
+	h->nbox = (h->row_bytes + 127) / 128;
+	const int nco_n = cfg->fs / VDL2_STEPRATE;	/* d8psk.c:348 */
+	h->nco_entries = (cfg->format == VDL2_FMT_CF32) ? nco_n : nco_n / 2;
+	h->n_sm = prop.multiProcessorCount;
+
+	/* dump schedule sanity: exactly 84 dumps per row, clock back at 0, <= 1 boundary per chunk */
+	{
+		int clk = 0, k = 0, lastc = -1;
+		for (int n = 0; n < h->row_samples; n++) {
+			clk += 21;
+			if (clk >= (int)cfg->sdrclk) {
+				clk %= (int)cfg->sdrclk;
+				k++;
+				if (n / h->spc == lastc) {
+					delete h;
+					return fail(NULL, "vdl2_create: two dump boundaries in one chunk (fs too low)");
+				}
+				lastc = n / h->spc;
+			}
+		}
+		if (k != VDL2_DUMPS_PER_ROW || clk != 0) {
+			delete h;
+			return fail(NULL, "vdl2_create: fs=%u sdrclk=%u gives %d dumps/ms (clk %d), need 84 (0)", cfg->fs, cfg->sdrclk, k, clk);
+		}
+	}
+
+	Vdl2Tables *tab = new Vdl2Tables();
+	build_tables(*tab, h);
+	e = (cudaError_t) vdl2_kernel_upload_tables(tab);
+	delete tab;
+	if (e != cudaSuccess) {
+		delete h;
+		return fail(NULL, "vdl2_create: constant table upload failed: %s", cudaGetErrorString(e));
+	}
+
+	h->smem = vdl2_kernel_smem_bytes(h->nco_entries);
+	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->smem, &h->ctas_per_sm);
+	if (e != cudaSuccess || h->ctas_per_sm < 1) {
+		delete h;
+		return fail(NULL, "vdl2_create: kernel does not fit (smem %d B): %s", h->smem, cudaGetErrorString(e));
+	}
+	h->grid = h->n_sm * h->ctas_per_sm;
+	h->st.n_sm = h->n_sm;
+	h->st.smem_bytes = h->smem;
+
+	CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CK(h, cudaEventCreate(&h->ev0));
+	CK(h, cudaEventCreate(&h->ev1));
+
+	const int nch = cfg->nch;
+	/* per-channel state: zero, then what initD8psk / initVdlm2 set (d8psk.c:28-37, vdlm2.c:167) */
+	std::vector < Vdl2ChanState > st(nch);
+	memset(st.data(), 0, sizeof(Vdl2ChanState) * nch);
+	for (int c = 0; c < nch; c++) {
+		st[c].perr = 100.f;
+		st[c].state = VDL2_ST_WSYNC;
+		st[c].chn = chans[c].chn;
+		st[c].Fr = chans[c].Fr;
+		st[c].sync_dump = -1;
+	}
+	CK(h, cudaMalloc(&h->d_state, sizeof(Vdl2ChanState) * nch));
+	CK(h, cudaMemcpy(h->d_state, st.data(), sizeof(Vdl2ChanState) * nch, cudaMemcpyHostToDevice));
+
+	/* NCO tables, d8psk.c:353-357 */
+	std::vector < float4 > wt((size_t) nch * h->nco_entries);
+	for (int c = 0; c < nch; c++) {
+		const float Fo = (float)((float)chans[c].Fo / (float)(cfg->fs) * 2.0 * M_PI);
+		std::vector < float >wr(nco_n), wi(nco_n);
+		for (int n = 0; n < nco_n; n++) {
+			/* cexpf(-n*Fo*I) = (cosf(a), sinf(a)) with the float product a = -n*Fo; glibc's
+			   cexpf evaluates exactly this pair (checked bit for bit in tests/test_oracle.py) */
+			const float a = (float)(-n) * Fo;
+			wr[n] = cosf(a);
+			wi[n] = sinf(a);
+		}
+		float4 *dst = wt.data() + (size_t) c * h->nco_entries;
+		if (cfg->format == VDL2_FMT_CF32) {
+			for (int n = 0; n < nco_n; n++)
+				dst[n] = make_float4(wr[n], wr[n], wi[n], wi[n]);
+		} else {
+			for (int p = 0; p < nco_n / 2; p++)
+				dst[p] = make_float4(wr[2 * p], wr[2 * p + 1], wi[2 * p], wi[2 * p + 1]);
+		}
+	}
+	CK(h, cudaMalloc(&h->d_wtab, sizeof(float4) * wt.size()));
+	CK(h, cudaMemcpy(h->d_wtab, wt.data(), sizeof(float4) * wt.size(), cudaMemcpyHostToDevice));
+
+	CK(h, cudaMalloc(&h->d_ticket, 64));
+	CK(h, cudaMemset(h->d_ticket, 0, 64));
+	h->d_outq_count = h->d_ticket + 4;
+	h->d_dropped = h->d_ticket + 8;
+	CK(h, cudaMalloc(&h->d_progress, sizeof(int) * nch));
+	CK(h, cudaMalloc(&h->d_curblk, (size_t) nch * 2048));
+	CK(h, cudaMemset(h->d_curblk, 0, (size_t) nch * 2048));
+	h->outq_cap = cfg->max_blocks > 0 ? (unsigned)cfg->max_blocks : (unsigned)std::max(4096, nch * 8);
+	CK(h, cudaMalloc(&h->d_outq, sizeof(Vdl2BlockRec) * (size_t) h->outq_cap));
+
+	const size_t maxs = cfg->max_samples ? cfg->max_samples : (size_t) 1 << 20;
+	const size_t max_rows = maxs / h->row_samples + 2;
+	h->cap_dumps = h->cap_steps = h->cap_syncs = h->cap_syms = 0;
+	h->d_tap_dumps = NULL;
+	h->d_tap_steps = NULL;
+	h->d_tap_syncs = NULL;
+	h->d_tap_syms = NULL;
+	if (cfg->taps & VDL2_TAP_DUMPS) {
+		h->cap_dumps = (unsigned)(max_rows * VDL2_DUMPS_PER_ROW);
+		CK(h, cudaMalloc(&h->d_tap_dumps, sizeof(float2) * (size_t) h->cap_dumps * nch));
+	}
+	if (cfg->taps & VDL2_TAP_STEPS) {
+		h->cap_steps = (unsigned)(max_rows * VDL2_DUMPS_PER_ROW / 2 + 64);
+		CK(h, cudaMalloc(&h->d_tap_steps, sizeof(Vdl2StepRec) * (size_t) h->cap_steps * nch));
+	}
+	if (cfg->taps & VDL2_TAP_SYNCS) {
+		h->cap_syncs = (unsigned)(max_rows * VDL2_DUMPS_PER_ROW / 64 + 64);
+		CK(h, cudaMalloc(&h->d_tap_syncs, sizeof(Vdl2SyncRec) * (size_t) h->cap_syncs * nch));
+	}
+	if (cfg->taps & VDL2_TAP_SYMS) {
+		h->cap_syms = (unsigned)(max_rows * VDL2_DUMPS_PER_ROW / 8 + 64);
+		CK(h, cudaMalloc(&h->d_tap_syms, sizeof(Vdl2SymRec) * (size_t) h->cap_syms * nch));
+	}
+
+	/* staging: room for a carried tail (< 1 row) plus one call */
+	h->stage_pitch = ((maxs + h->row_samples) * h->bytes_per_sample + 255) & ~(size_t) 255;
+	CK(h, cudaMalloc(&h->d_stage, h->stage_pitch * h->nstreams));
+
+	cudaDriverEntryPointQueryResult qres;
+	h->encode_fn = NULL;
+	CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_fn, cudaEnableDefault, &qres));
+	if (!h->encode_fn || qres != cudaDriverEntryPointSuccess)
+		return fail(h, "vdl2_create: cuTensorMapEncodeTiled not available from the driver");
+	*out = h;
+	return 0;
+}
+
+extern "C" int vdl2_destroy(vdl2gpu_t * h)
+{
+	if (!h)
+		return 0;
+	cudaSetDevice(h->cfg.device);
+	cudaStreamSynchronize(h->stream);
+	cudaFree(h->d_state);
+	cudaFree(h->d_wtab);
+	cudaFree(h->d_ticket);
+	cudaFree(h->d_progress);
+	cudaFree(h->d_curblk);
+	cudaFree(h->d_outq);
+	cudaFree(h->d_tap_dumps);
+	cudaFree(h->d_tap_steps);
+	cudaFree(h->d_tap_syncs);
+	cudaFree(h->d_tap_syms);
+	cudaFree(h->d_stage);
+	cudaEventDestroy(h->ev0);
+	cudaEventDestroy(h->ev1);
+	cudaStreamDestroy(h->stream);
+	delete h;
+	return 0;
+}
+
+typedef CUresult(*encode_tiled_t) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+				   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+				   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+/* demodulate `nrows` complete rows starting at `base` (device), streams `pitch` bytes apart */
+static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
+{
+	if (nrows <= 0)
+		return 0;
+	if (((uintptr_t) base & 15) || (pitch & 15))
+		return fail(h, "input base/pitch must be 16-byte aligned for TMA (base %p pitch %zu)", base, pitch);
+	CUtensorMap tmap;
+	const cuuint64_t dims[3] = { (cuuint64_t) (h->row_bytes / 4), (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
+	const cuuint64_t strides[2] = { (cuuint64_t) h->row_bytes, (cuuint64_t) pitch };
+	const cuuint32_t box[3] = { 32, 32, 1 };
+	const cuuint32_t estr[3] = { 1, 1, 1 };
+	CUresult r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr,
+						     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+						     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+		return fail(h, "cuTensorMapEncodeTiled failed (%d): rows=%d row_bytes=%d pitch=%zu", (int)r, nrows, h->row_bytes, pitch);
+
+	Vdl2KParams kp;
+	memset(&kp, 0, sizeof kp);
+	kp.nch = h->cfg.nch;
+	kp.ch_per_stream = h->cfg.ch_per_stream;
+	kp.nrows = nrows;
+	kp.ntiles = (nrows + VDL2_ROWS_PER_TILE - 1) / VDL2_ROWS_PER_TILE;
+	kp.chunks_per_row = h->chunks_per_row;
+	kp.nbox = h->nbox;
+	kp.nco_pairs = h->nco_entries;
+	kp.dump_base = h->rows_done * VDL2_DUMPS_PER_ROW;
+	kp.state = h->d_state;
+	kp.wtab = h->d_wtab;
+	kp.ticket = h->d_ticket;
+	kp.progress = h->d_progress;
+	kp.curblk = h->d_curblk;
+	kp.outq = h->d_outq;
+	kp.outq_count = h->d_outq_count;
+	kp.outq_cap = h->outq_cap;
+	kp.dropped = h->d_dropped;
+	kp.taps = h->cfg.taps;
+	kp.tap_dumps = h->d_tap_dumps;
+	kp.tap_steps = h->d_tap_steps;
+	kp.tap_syncs = h->d_tap_syncs;
+	kp.tap_syms = h->d_tap_syms;
+	kp.cap_dumps = h->cap_dumps;
+	kp.cap_steps = h->cap_steps;
+	kp.cap_syncs = h->cap_syncs;
+	kp.cap_syms = h->cap_syms;
+
+	CK(h, cudaMemsetAsync(h->d_ticket, 0, 4, h->stream));
+	CK(h, cudaMemsetAsync(h->d_progress, 0, sizeof(int) * h->cfg.nch, h->stream));
+	const long long items = (long long)kp.ntiles * kp.nch;
+	const int grid = (int)std::min < long long >(items, h->grid);
+	CK(h, cudaEventRecord(h->ev0, h->stream));
+	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, &tmap, &kp, grid, h->smem, h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "kernel launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaEventRecord(h->ev1, h->stream));
+	h->ev_valid = true;
+	h->st.kernel_launches++;
+	h->st.grid = grid;
+	h->rows_done += nrows;
+	h->st.samples_done += (uint64_t) nrows * h->row_samples;
+	return 0;
+}
+
+/* after new samples were placed behind the carried tail in the staging buffer */
+static int run_staged(vdl2gpu * h, size_t total)
+{
+	const int nrows = (int)(total / h->row_samples);
+	if (run_rows(h, h->d_stage, h->stage_pitch, nrows))
+		return 1;
+	const size_t used = (size_t) nrows * h->row_samples;
+	const size_t tail = total - used;
+	if (tail && used) {	/* tail < one row <= used: source and destination never overlap */
+		CK(h, cudaMemcpy2DAsync(h->d_stage, h->stage_pitch, h->d_stage + used * h->bytes_per_sample, h->stage_pitch,
+					tail * h->bytes_per_sample, h->nstreams, cudaMemcpyDeviceToDevice, h->stream));
+	}
+	h->carry = tail;
+	return 0;
+}
+
+extern "C" int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes)
+{
+	if (!h || !iq)
+		return fail(h, "vdl2_process_host: null argument");
+	CK(h, cudaSetDevice(h->cfg.device));
+	const size_t bps = h->bytes_per_sample;
+	if ((h->carry + nsamples) * bps > h->stage_pitch)
+		return fail(h, "vdl2_process_host: %zu samples exceed max_samples of the handle", nsamples);
+	if (h->nstreams > 1 && pitch_bytes < nsamples * bps)
+		return fail(h, "vdl2_process_host: pitch %zu smaller than a stream (%zu bytes)", pitch_bytes, nsamples * bps);
+	h->st.samples_in += nsamples;
+	if (nsamples)
+		CK(h, cudaMemcpy2DAsync(h->d_stage + h->carry * bps, h->stage_pitch, iq, h->nstreams > 1 ? pitch_bytes : nsamples * bps,
+					nsamples * bps, h->nstreams, cudaMemcpyHostToDevice, h->stream));
+	if (run_staged(h, h->carry + nsamples))
+		return 1;
+	CK(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int vdl2_process_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes)
+{
+	if (!h || !d_iq)
+		return fail(h, "vdl2_process_device: null argument");
+	CK(h, cudaSetDevice(h->cfg.device));
+	const size_t bps = h->bytes_per_sample;
+	h->st.samples_in += nsamples;
+	const bool aligned = (((uintptr_t) d_iq & 15) == 0) && ((pitch_bytes & 15) == 0 || h->nstreams == 1);
+	if (h->carry == 0 && nsamples % h->row_samples == 0 && aligned) {
+		/* zero copy: the TMA descriptor points straight at the caller's buffer */
+		const int nrows = (int)(nsamples / h->row_samples);
+		return run_rows(h, d_iq, h->nstreams == 1 ? (size_t) h->row_bytes * nrows : pitch_bytes, nrows);
+	}
+	if ((h->carry + nsamples) * bps > h->stage_pitch)
+		return fail(h, "vdl2_process_device: %zu samples exceed max_samples of the handle", nsamples);
+	if (nsamples)
+		CK(h, cudaMemcpy2DAsync(h->d_stage + h->carry * bps, h->stage_pitch, d_iq, h->nstreams > 1 ? pitch_bytes : nsamples * bps,
+					nsamples * bps, h->nstreams, cudaMemcpyDeviceToDevice, h->stream));
+	return run_staged(h, h->carry + nsamples);
+}
+
+extern "C" int vdl2_sync(vdl2gpu_t * h)
+{
+	if (!h)
+		return 1;
+	CK(h, cudaSetDevice(h->cfg.device));
+	CK(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out)
+{
+	if (!h || !n_out)
+		return fail(h, "vdl2_drain_blocks: null argument");
+	*n_out = 0;
+	CK(h, cudaSetDevice(h->cfg.device));
+	CK(h, cudaStreamSynchronize(h->stream));
+	unsigned cnt[8];
+	CK(h, cudaMemcpy(cnt, h->d_outq_count, sizeof cnt, cudaMemcpyDeviceToHost));
+	unsigned n = std::min(cnt[0], h->outq_cap);
+	h->st.blocks_dropped += cnt[4];
+	if (n == 0) {
+		if (cnt[4])
+			CK(h, cudaMemset(h->d_dropped, 0, 4));
+		return 0;
+	}
+	if (!out || max < (int)n)
+		return fail(h, "vdl2_drain_blocks: %u blocks pending, room for %d", n, max);
+	CK(h, cudaMemcpy(out, h->d_outq, sizeof(Vdl2BlockRec) * n, cudaMemcpyDeviceToHost));
+	CK(h, cudaMemset(h->d_outq_count, 0, 4));
+	if (cnt[4])
+		CK(h, cudaMemset(h->d_dropped, 0, 4));
+	std::stable_sort(out, out + n,[](const vdl2_block_t & a, const vdl2_block_t & b) {
+			 return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : a.chn < b.chn;}
+	);
+	h->st.blocks_out += n;
+	*n_out = (int)n;
+	return 0;
+}
+
+template < class T > static int read_tap(vdl2gpu * h, int ch, T * d_base, unsigned cap, size_t off_count, T * out, size_t max,
+					  size_t *n_out)
+{
+	if (!h || !n_out)
+		return fail(h, "vdl2_read_*: null argument");
+	*n_out = 0;
+	if (!d_base)
+		return fail(h, "vdl2_read_*: this tap was not enabled in vdl2_config_t.taps");
+	if (ch < 0 || ch >= h->cfg.nch)
+		return fail(h, "vdl2_read_*: channel %d out of range", ch);
+	CK(h, cudaSetDevice(h->cfg.device));
+	CK(h, cudaStreamSynchronize(h->stream));
+	unsigned n = 0;
+	char *cnt = (char *)(h->d_state + ch) + off_count;
+	CK(h, cudaMemcpy(&n, cnt, 4, cudaMemcpyDeviceToHost));
+	if (n > cap)
+		return fail(h, "vdl2_read_*: tap overflow on channel %d (%u records, capacity %u); read more often", ch, n, cap);
+	if (n > max)
+		return fail(h, "vdl2_read_*: %u records pending, room for %zu", n, max);
+	if (n)
+		CK(h, cudaMemcpy(out, d_base + (size_t) ch * cap, sizeof(T) * n, cudaMemcpyDeviceToHost));
+	CK(h, cudaMemset(cnt, 0, 4));
+	*n_out = n;
+	return 0;
+}
+
+extern "C" int vdl2_read_dumps(vdl2gpu_t * h, int ch, float *iq_out, size_t max, size_t *n_out)
+{
+	return read_tap < float2 > (h, ch, h ? h->d_tap_dumps : NULL, h ? h->cap_dumps : 0, offsetof(Vdl2ChanState, n_dumps),
+				    (float2 *) iq_out, max, n_out);
+}
+
+extern "C" int vdl2_read_steps(vdl2gpu_t * h, int ch, vdl2_step_t * out, size_t max, size_t *n_out)
+{
+	return read_tap < Vdl2StepRec > (h, ch, h ? h->d_tap_steps : NULL, h ? h->cap_steps : 0, offsetof(Vdl2ChanState, n_steps),
+					 (Vdl2StepRec *) out, max, n_out);
+}
+
+extern "C" int vdl2_read_syncs(vdl2gpu_t * h, int ch, vdl2_sync_t * out, size_t max, size_t *n_out)
+{
+	return read_tap < Vdl2SyncRec > (h, ch, h ? h->d_tap_syncs : NULL, h ? h->cap_syncs : 0, offsetof(Vdl2ChanState, n_syncs),
+					 (Vdl2SyncRec *) out, max, n_out);
+}
+
+extern "C" int vdl2_read_syms(vdl2gpu_t * h, int ch, vdl2_sym_t * out, size_t max, size_t *n_out)
+{
+	return read_tap < Vdl2SymRec > (h, ch, h ? h->d_tap_syms : NULL, h ? h->cap_syms : 0, offsetof(Vdl2ChanState, n_syms),
+					(Vdl2SymRec *) out, max, n_out);
+}
+
+extern "C" int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st)
+{
+	if (!h || !st)
+		return 1;
+	CK(h, cudaSetDevice(h->cfg.device));
+	if (h->ev_valid) {
+		CK(h, cudaEventSynchronize(h->ev1));
+		float ms = 0;
+		CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+		h->st.last_kernel_ms = ms;
+	}
+	*st = h->st;
+	return 0;
+}
+
+extern "C" void *vdl2_cuda_stream(vdl2gpu_t * h)
+{
+	return h ? (void *)h->stream : NULL;
+}

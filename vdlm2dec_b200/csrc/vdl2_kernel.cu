@@ -1,0 +1,478 @@
+/*
+ * vdl2_kernel.cu -- the fused sm_100a front-end kernel (channeliser + D8PSK demodulator).
+ *
+ * One persistent single-warp CTA per resident slot; work items are (tile, channel) pairs
+ * handed out tile-major by an atomic ticket.  A tile is 32 rows of 1 ms of one channel's
+ * input stream (one row per lane), because 1 ms is the joint period of the reference's
+ * 21/SDRCLK dump clock and its 25 kHz-periodic NCO table (d8psk.c:348-381, SURVEY.md
+ * appendix A.1): every lane then runs the SAME dump schedule with the SAME oscillator
+ * value at every step, so the schedule lives in constant memory, the NCO table is a
+ * warp-broadcast shared-memory read, and the tap dot products need no cross-lane traffic.
+ *
+ *   phase 1 (channeliser, rtl.c:285-292 + d8psk.c:366-381): a 3-D TMA tensor map views a
+ *     stream as [stream][row][row bytes]; `cp.async.bulk.tensor` boxes of 32 rows x 128 B
+ *     land 128B-swizzled in a 3-stage mbarrier ring, which transposes time-major HBM into
+ *     lane-major shared memory: lane r reads 16-byte chunk j of its row at (j ^ (r&7))<<4,
+ *     conflict free.  Bytes are widened with PRMT magic-number tricks (exact), the complex
+ *     MAC runs as packed FFMA2 on sample pairs, dumps go to shared memory in time order.
+ *   phase 2 (demodulator): vdl2_demod.cuh, lanes over consecutive steps / symbols.
+ *
+ * Phase 1 needs no channel state, so a warp mixes tile t of a channel while another warp
+ * still demodulates tile t-1; only phase 2 waits on the per-channel progress flag.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vdl2_demod.cuh"
+#include "vdl2_kernel.h"
+
+namespace vdl2 {
+
+#define NSTAGE VDL2_NSTAGE
+#define STAGE_BYTES 4096
+
+/* ------------------------------------------------------------------ PTX helpers */
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;"::"r" (bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"::"r" (bar), "r"(bytes):"memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	asm volatile ("{\n"
+		      ".reg .pred p;\n"
+		      "WAIT_%=:\n"
+		      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		      "@p bra DONE_%=;\n" "bra WAIT_%=;\n" "DONE_%=:\n" "}"::"r" (bar), "r"(parity):"memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2)
+{
+	asm volatile ("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+		      " [%0], [%1, {%3, %4, %5}], [%2];"::"r" (dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+		      :"memory");
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a);
+	unsigned long long rb = *reinterpret_cast < unsigned long long *>(&b);
+	unsigned long long rc = *reinterpret_cast < unsigned long long *>(&c);
+	unsigned long long rd;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(rd):"l"(ra), "l"(rb), "l"(rc));
+	return *reinterpret_cast < float2 * >(&rd);
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a);
+	unsigned long long rb = *reinterpret_cast < unsigned long long *>(&b);
+	unsigned long long rd;
+	asm("add.rn.f32x2 %0, %1, %2;":"=l"(rd):"l"(ra), "l"(rb));
+	return *reinterpret_cast < float2 * >(&rd);
+}
+
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a);
+	unsigned long long rb = *reinterpret_cast < unsigned long long *>(&b);
+	unsigned long long rd;
+	asm("mul.rn.f32x2 %0, %1, %2;":"=l"(rd):"l"(ra), "l"(rb));
+	return *reinterpret_cast < float2 * >(&rd);
+}
+
+/* ------------------------------------------------------------------ phase 1: channeliser */
+struct MixAcc {			/* partial sums of one dump; .x/.y = even/odd sample of a pair */
+	float2 A, B, C, G;	/* A: xr*wr  B: xi*wi  C: xr*wi  G: xi*wr */
+};
+
+__device__ __forceinline__ void acc_zero(MixAcc & a)
+{
+	a.A = a.B = a.C = a.G = make_float2(0.f, 0.f);
+}
+
+/* close a dump: D = sum / nf (d8psk.c:377), store in time order */
+__device__ __forceinline__ void dump_close(MixAcc & a, float2 * sdrow, int &k)
+{
+	const float s = c_tab.scale[k];
+	const float re = (a.A.x + a.A.y) - (a.B.x + a.B.y);
+	const float im = (a.C.x + a.C.y) + (a.G.x + a.G.y);
+	sdrow[k] = fmul2(make_float2(re, im), make_float2(s, s));
+	k++;
+	acc_zero(a);
+}
+
+/* 4 bytes (I0 Q0 I1 Q1) -> exact floats.  PRMT builds 0x4B0000uu = 2^23 + u, one packed
+   add removes the bias; cu8 then subtracts 127.37f exactly like rtl.c:287-289 (u - 127.37f
+   is exact in fp32 for all 256 inputs), cs8 is biased by 128 through the sign-bit flip. */
+template < int FMT > __device__ __forceinline__ void cvt_pair8(uint32_t w, float2 & xr, float2 & xi)
+{
+	if (FMT == VDL2_FMT_CS8)
+		w ^= 0x80808080u;
+	const uint32_t magic = 0x4B000000u;
+	xr.x = __uint_as_float(__byte_perm(w, magic, 0x7440));
+	xi.x = __uint_as_float(__byte_perm(w, magic, 0x7441));
+	xr.y = __uint_as_float(__byte_perm(w, magic, 0x7442));
+	xi.y = __uint_as_float(__byte_perm(w, magic, 0x7443));
+	if (FMT == VDL2_FMT_CS8) {
+		const float2 m = make_float2(-8388736.f, -8388736.f);	/* -(2^23 + 128) */
+		xr = fadd2(xr, m);
+		xi = fadd2(xi, m);
+	} else {
+		const float2 m = make_float2(-8388608.f, -8388608.f);
+		const float2 o = make_float2(-127.37f, -127.37f);
+		xr = fadd2(fadd2(xr, m), o);
+		xi = fadd2(fadd2(xi, m), o);
+	}
+}
+
+/* one sample pair with its oscillator pair W = (re[n], re[n+1], im[n], im[n+1]).
+   SPLIT = 0: both samples in the current dump; 1: dump boundary between them; 2: after them */
+template < int SPLIT > __device__ __forceinline__ void mac_pair(MixAcc & a, float2 xr, float2 xi, float4 W, float2 * sdrow,
+								 int &k)
+{
+	if (SPLIT == 1) {
+		a.A.x = fmaf(xr.x, W.x, a.A.x);
+		a.B.x = fmaf(xi.x, W.z, a.B.x);
+		a.C.x = fmaf(xr.x, W.z, a.C.x);
+		a.G.x = fmaf(xi.x, W.x, a.G.x);
+		dump_close(a, sdrow, k);
+		a.A.y = xr.y * W.y;
+		a.B.y = xi.y * W.w;
+		a.C.y = xr.y * W.w;
+		a.G.y = xi.y * W.y;
+	} else {
+		const float2 wr = make_float2(W.x, W.y), wi = make_float2(W.z, W.w);
+		a.A = ffma2(xr, wr, a.A);
+		a.B = ffma2(xi, wi, a.B);
+		a.C = ffma2(xr, wi, a.C);
+		a.G = ffma2(xi, wr, a.G);
+		if (SPLIT == 2)
+			dump_close(a, sdrow, k);
+	}
+}
+
+/* a 16-byte chunk of 8-bit IQ = 8 samples = 4 pairs; E = last sample of the current dump
+   inside this chunk (0..7), or 8 if the dump continues */
+template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+{
+	const uint32_t d[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+	for (int p = 0; p < 4; p++) {
+		float2 xr, xi;
+		cvt_pair8 < FMT > (d[p], xr, xi);
+		const float4 W = w[p];
+		if (E == 2 * p)
+			mac_pair < 1 > (a, xr, xi, W, sdrow, k);
+		else if (E == 2 * p + 1)
+			mac_pair < 2 > (a, xr, xi, W, sdrow, k);
+		else
+			mac_pair < 0 > (a, xr, xi, W, sdrow, k);
+	}
+}
+
+template < int FMT > __device__ __forceinline__ void chunk8_dispatch(int kind, MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								      int &k)
+{
+	if (kind == 8) {
+		chunk8 < FMT, 8 > (a, v, w, sdrow, k);
+		return;
+	}
+	switch (kind) {
+	case 0: chunk8 < FMT, 0 > (a, v, w, sdrow, k); break;
+	case 1: chunk8 < FMT, 1 > (a, v, w, sdrow, k); break;
+	case 2: chunk8 < FMT, 2 > (a, v, w, sdrow, k); break;
+	case 3: chunk8 < FMT, 3 > (a, v, w, sdrow, k); break;
+	case 4: chunk8 < FMT, 4 > (a, v, w, sdrow, k); break;
+	case 5: chunk8 < FMT, 5 > (a, v, w, sdrow, k); break;
+	case 6: chunk8 < FMT, 6 > (a, v, w, sdrow, k); break;
+	default: chunk8 < FMT, 7 > (a, v, w, sdrow, k); break;
+	}
+}
+
+/* complex float input (the reference's Cbuff, vdlm2.h:89): a chunk is 2 samples; the
+   oscillator table is stored duplicated, W = (re, re, im, im) per sample, so that the
+   natural (I, Q) register pair feeds FFMA2 directly:
+   A += (I,Q)*(re,re), C += (I,Q)*(im,im);  D = (A.x - C.y) + i (C.x + A.y) */
+template < int E > __device__ __forceinline__ void chunk_cf32(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+{
+	const float2 x0 = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+	const float2 x1 = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+	const float4 W0 = w[0], W1 = w[1];
+	a.A = ffma2(x0, make_float2(W0.x, W0.y), a.A);
+	a.C = ffma2(x0, make_float2(W0.z, W0.w), a.C);
+	if (E == 0) {
+		a.B = make_float2(a.C.y, 0.f);	/* fold into the common close: re = A.x+A.y - (B.x+B.y) */
+		a.G = make_float2(a.A.y, 0.f);
+		a.A.y = 0.f;
+		a.C.y = 0.f;
+		dump_close(a, sdrow, k);
+	}
+	a.A = ffma2(x1, make_float2(W1.x, W1.y), a.A);
+	a.C = ffma2(x1, make_float2(W1.z, W1.w), a.C);
+	if (E == 1) {
+		a.B = make_float2(a.C.y, 0.f);
+		a.G = make_float2(a.A.y, 0.f);
+		a.A.y = 0.f;
+		a.C.y = 0.f;
+		dump_close(a, sdrow, k);
+	}
+}
+
+template < int FMT > struct FmtTraits;
+template <> struct FmtTraits <VDL2_FMT_CU8 > { static constexpr int wper_chunk = 4; };
+template <> struct FmtTraits <VDL2_FMT_CS8 > { static constexpr int wper_chunk = 4; };
+template <> struct FmtTraits <VDL2_FMT_CF32 > { static constexpr int wper_chunk = 2; };
+
+template < int FMT > __device__ __forceinline__ void chunk_any(int kind, MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+{
+	if (FMT == VDL2_FMT_CF32) {
+		if (kind == 0)
+			chunk_cf32 < 0 > (a, v, w, sdrow, k);
+		else if (kind == 1)
+			chunk_cf32 < 1 > (a, v, w, sdrow, k);
+		else
+			chunk_cf32 < 2 > (a, v, w, sdrow, k);
+	} else {
+		chunk8_dispatch < FMT > (kind, a, v, w, sdrow, k);
+	}
+}
+
+/* ------------------------------------------------------------------ the kernel */
+template < int FMT > __global__ void __launch_bounds__(32, 1)
+vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const int lane = threadIdx.x;
+	unsigned char *stage0 = smem;
+	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + NSTAGE * STAGE_BYTES);
+	float2 *sd = reinterpret_cast < float2 * >(smem + NSTAGE * STAGE_BYTES + 64);
+	float *phb = reinterpret_cast < float *>(sd + VDL2_HIST + VDL2_TILE_DUMPS);
+	float *hv = phb + 96;
+	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
+
+	if ((smem_u32(smem) & 1023u) != 0)
+		__trap();	/* the 128B swizzle pattern assumes 1 KiB aligned stages */
+	if (lane == 0) {
+		for (int s = 0; s < NSTAGE; s++)
+			mbar_init(smem_u32(bars + s), 1);
+		asm volatile ("fence.mbarrier_init.release.cluster;":::"memory");
+	}
+	__syncwarp();
+
+	uint32_t phases = 0;	/* parity bit per stage */
+	const int nitems = kp.ntiles * kp.nch;
+	const int wpc = FmtTraits < FMT >::wper_chunk;
+	const int last_chunks = kp.chunks_per_row - 8 * (kp.nbox - 1);
+	const uint32_t l7 = (uint32_t) (lane & 7);
+	float2 *sdrow = sd + VDL2_HIST + VDL2_DUMPS_PER_ROW * lane;
+
+	for (;;) {
+		int item = 0;
+		if (lane == 0)
+			item = (int)atomicAdd(kp.ticket, 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= nitems)
+			break;
+		const int tile = item / kp.nch;
+		const int ch = item - tile * kp.nch;
+		const int stream = ch / kp.ch_per_stream;
+		const int row0 = tile * VDL2_ROWS_PER_TILE;
+		const int nrows = min(VDL2_ROWS_PER_TILE, kp.nrows - row0);
+		const int nd = nrows * VDL2_DUMPS_PER_ROW;
+
+		/* prologue: first boxes in flight, oscillator table to shared memory */
+		if (lane == 0) {
+			for (int b = 0; b < NSTAGE && b < kp.nbox; b++) {
+				const uint32_t bar = smem_u32(bars + b);
+				mbar_expect_tx(bar, STAGE_BYTES);
+				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream);
+			}
+		}
+		for (int i = lane; i < kp.nco_pairs; i += 32)
+			wsm[i] = kp.wtab[(size_t) ch * kp.nco_pairs + i];
+		__syncwarp();
+
+		/* ---- phase 1 ---- */
+		MixAcc acc;
+		acc_zero(acc);
+		int k = 0, cidx = 0, widx = 0;
+		for (int b = 0; b < kp.nbox; b++) {
+			const int slot = b % NSTAGE;
+			mbar_wait(smem_u32(bars + slot), (phases >> slot) & 1u);
+			phases ^= 1u << slot;
+			const unsigned char *rowp = stage0 + slot * STAGE_BYTES + lane * 128;
+			const int nchunk = (b == kp.nbox - 1) ? last_chunks : 8;
+#pragma unroll 1
+			for (int j = 0; j < nchunk; j++) {
+				const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
+				const int kind = c_tab.sched[cidx++];
+				chunk_any < FMT > (kind, acc, v, wsm + widx, sdrow, k);
+				widx += wpc;
+				if (widx >= kp.nco_pairs)
+					widx = 0;
+			}
+			__syncwarp();
+			if (lane == 0 && b + NSTAGE < kp.nbox) {
+				const uint32_t bar = smem_u32(bars + slot);
+				mbar_expect_tx(bar, STAGE_BYTES);
+				tma_load_3d(smem_u32(stage0 + slot * STAGE_BYTES), &tmap, bar, (b + NSTAGE) * 32, row0, stream);
+			}
+		}
+		__syncwarp();
+
+		/* ---- wait for the previous tile of this channel, load its state ---- */
+		if (lane == 0) {
+			const volatile int *pr = kp.progress + ch;
+			while (*pr < tile)
+				__nanosleep(200);
+		}
+		__syncwarp();
+		__threadfence();
+		Vdl2ChanState *gs = kp.state + ch;
+		if (lane < VDL2_HIST)
+			sd[lane] = make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane));
+		phb[lane] = __ldcg(gs->ph + lane);
+		phb[lane + 32] = __ldcg(gs->ph + lane + 32);
+		if (lane < 28)
+			hv[lane] = __ldcg(gs->hv + lane);
+		ChanRegs R;
+		R.perr = __ldcg(&gs->perr);
+		R.p2err = __ldcg(&gs->p2err);
+		R.pfr = __ldcg(&gs->pfr);
+		R.df = __ldcg(&gs->df);
+		R.P1 = __ldcg(&gs->P1);
+		R.ppm = __ldcg(&gs->ppm);
+		R.clk = __ldcg(&gs->clk);
+		R.state = __ldcg(&gs->state);
+		R.symidx = __ldcg(&gs->symidx);
+		R.nbrow = __ldcg(&gs->nbrow);
+		R.nlbyte = __ldcg(&gs->nlbyte);
+		R.bytes_done = __ldcg(&gs->bytes_done);
+		R.bitacc = __ldcg(&gs->bitacc);
+		R.nbitacc = __ldcg(&gs->nbitacc);
+		R.sync_dump = __ldcg(&gs->sync_dump);
+		R.n_steps = __ldcg(&gs->n_steps);
+		R.n_syncs = __ldcg(&gs->n_syncs);
+		R.n_syms = __ldcg(&gs->n_syms);
+		unsigned n_dumps = __ldcg(&gs->n_dumps);
+		const int chn = __ldcg(&gs->chn), Fr = __ldcg(&gs->Fr);
+		__syncwarp();
+
+		const long long dump_base = kp.dump_base + (long long)row0 * VDL2_DUMPS_PER_ROW;
+		if (kp.taps & VDL2_TAP_DUMPS_BIT) {
+			float2 *dst = kp.tap_dumps + (size_t) ch * kp.cap_dumps;
+			for (int i = lane; i < nd; i += 32)
+				if (n_dumps + i < kp.cap_dumps)
+					dst[n_dumps + i] = sd[VDL2_HIST + i];
+			n_dumps += nd;
+		}
+
+		/* ---- phase 2 ---- */
+		demod_tile(kp, ch, chn, Fr, R, sd, phb, hv, nd, dump_base);
+		__syncwarp();
+
+		/* ---- store state, release the channel ---- */
+		if (lane < VDL2_HIST) {
+			const float2 h = sd[nd + lane];	/* last 16 dumps of the tile */
+			gs->hist_re[lane] = h.x;
+			gs->hist_im[lane] = h.y;
+		}
+		gs->ph[lane] = phb[lane];
+		gs->ph[lane + 32] = phb[lane + 32];
+		if (lane < 28)
+			gs->hv[lane] = hv[lane];
+		if (lane == 0) {
+			gs->perr = R.perr;
+			gs->p2err = R.p2err;
+			gs->pfr = R.pfr;
+			gs->df = R.df;
+			gs->P1 = R.P1;
+			gs->ppm = R.ppm;
+			gs->clk = R.clk;
+			gs->state = R.state;
+			gs->symidx = R.symidx;
+			gs->nbrow = R.nbrow;
+			gs->nlbyte = R.nlbyte;
+			gs->bytes_done = R.bytes_done;
+			gs->bitacc = R.bitacc;
+			gs->nbitacc = R.nbitacc;
+			gs->sync_dump = R.sync_dump;
+			gs->n_steps = R.n_steps;
+			gs->n_syncs = R.n_syncs;
+			gs->n_syms = R.n_syms;
+			gs->n_dumps = n_dumps;
+		}
+		__threadfence();
+		__syncwarp();
+		if (lane == 0)
+			atomicExch(kp.progress + ch, tile + 1);
+		__syncwarp();
+	}
+}
+
+}				/* namespace vdl2 */
+
+/* ------------------------------------------------------------------ launch shims used by vdl2_host.cu */
+extern "C" int vdl2_kernel_smem_bytes(int nco_entries)
+{
+	return VDL2_NSTAGE * STAGE_BYTES + 64 + (VDL2_HIST + VDL2_TILE_DUMPS) * 8 + 96 * 4 + 32 * 4 + nco_entries * 16;
+}
+
+template < int FMT > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+{
+	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess)
+		return e;
+	vdl2::vdl2_frontend_kernel < FMT > <<<grid, 32, smem, st >>> (tmap, kp);
+	return cudaGetLastError();
+}
+
+extern "C" int vdl2_kernel_launch(int fmt, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream)
+{
+	const CUtensorMap & m = *reinterpret_cast < const CUtensorMap * >(tmap);
+	cudaStream_t st = (cudaStream_t) stream;
+	switch (fmt) {
+	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32 > (m, *kp, grid, smem, st);
+	}
+	return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm)
+{
+	cudaError_t e;
+	switch (fmt) {
+	case VDL2_FMT_CU8:
+		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CU8 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CU8 >, 32, smem);
+		break;
+	case VDL2_FMT_CS8:
+		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CS8 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CS8 >, 32, smem);
+		break;
+	case VDL2_FMT_CF32:
+		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CF32 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CF32 >, 32, smem);
+		break;
+	default:
+		return (int)cudaErrorInvalidValue;
+	}
+	return (int)e;
+}
+
+extern "C" int vdl2_kernel_upload_tables(const Vdl2Tables * t)
+{
+	return (int)cudaMemcpyToSymbol(c_tab, t, sizeof(Vdl2Tables));
+}

@@ -1,0 +1,19 @@
+/* vdl2_kernel.h -- internal interface between vdl2_host.cu and vdl2_kernel.cu */
+#ifndef VDL2_KERNEL_H
+#define VDL2_KERNEL_H
+#include "../../include/vdl2gpu.h"
+#include "vdl2_common.h"
+
+#define VDL2_NSTAGE 3		/* TMA boxes (32 rows x 128 B) in flight per warp */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int vdl2_kernel_smem_bytes(int nco_entries);
+int vdl2_kernel_launch(int fmt, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream);
+int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm);
+int vdl2_kernel_upload_tables(const struct Vdl2Tables *t);
+#ifdef __cplusplus
+}
+#endif
+#endif
