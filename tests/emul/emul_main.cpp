@@ -1,0 +1,178 @@
+/*
+ * tests/emul/emul_main.cpp -- TEST INFRASTRUCTURE: runs phase 2 of the kernel
+ * (vdl2_demod.cuh, unmodified) on the host through the fibre warp emulator.
+ * Input is a decimated 84 ksps stream (e.g. the oracle's tap T1); output are the same
+ * block / sync / symbol / step records the kernel writes.
+ */
+#include <ucontext.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "vdl2_demod.cuh"
+
+namespace vw {
+int g_lane;
+uint64_t g_xch[32];
+static ucontext_t g_main, g_ctx[32];
+static int g_arrived, g_gen, g_done[32];
+static void yield_() { swapcontext(&g_ctx[g_lane], &g_main); }
+void barrier()
+{
+	const int my = g_gen;
+	if (++g_arrived == 32) {
+		g_arrived = 0;
+		g_gen++;
+		return;
+	}
+	while (g_gen == my)
+		yield_();
+}
+}
+
+struct TileJob {
+	const Vdl2KParams *kp;
+	int ch, chn, Fr, nd;
+	long long dump_base;
+	float2 *sd;
+	float *phb, *hv;
+	vdl2::ChanRegs R0;
+	vdl2::ChanRegs Rout[32];
+};
+static TileJob *g_job;
+
+static void lane_main(int lane)
+{
+	TileJob *j = g_job;
+	vdl2::ChanRegs R = j->R0;
+	vdl2::demod_tile(*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->phb, j->hv, j->nd, j->dump_base);
+	j->Rout[lane] = R;
+	vw::g_done[lane] = 1;
+}
+
+static void run_warp(TileJob * job)
+{
+	static std::vector < char >stacks;
+	const size_t SS = 256 * 1024;
+	if (stacks.empty())
+		stacks.resize(32 * SS);
+	g_job = job;
+	vw::g_arrived = 0;
+	for (int i = 0; i < 32; i++) {
+		vw::g_done[i] = 0;
+		getcontext(&vw::g_ctx[i]);
+		vw::g_ctx[i].uc_stack.ss_sp = stacks.data() + i * SS;
+		vw::g_ctx[i].uc_stack.ss_size = SS;
+		vw::g_ctx[i].uc_link = &vw::g_main;
+		makecontext(&vw::g_ctx[i], (void (*)())lane_main, 1, i);
+	}
+	int live = 32;
+	while (live) {
+		live = 0;
+		for (int i = 0; i < 32; i++) {
+			if (vw::g_done[i])
+				continue;
+			vw::g_lane = i;
+			swapcontext(&vw::g_main, &vw::g_ctx[i]);
+			if (!vw::g_done[i])
+				live++;
+		}
+	}
+}
+
+static bool same_regs(const vdl2::ChanRegs & a, const vdl2::ChanRegs & b)
+{
+#define EQ(f) (memcmp(&a.f, &b.f, sizeof a.f) == 0)
+	return EQ(perr) && EQ(p2err) && EQ(pfr) && EQ(df) && EQ(P1) && EQ(ppm) && EQ(clk) && EQ(state) && EQ(symidx) && EQ(nbrow)
+	    && EQ(nlbyte) && EQ(bytes_done) && EQ(bitacc) && EQ(nbitacc) && EQ(sync_dump) && EQ(n_steps) && EQ(n_syncs) && EQ(n_syms);
+#undef EQ
+}
+
+static void build_tables()
+{
+	memset(&c_tab, 0, sizeof c_tab);
+	float mf[VDL2_MFLTLEN], sw[VDL2_NBPH];
+	static float soft[3][257];
+	vdl2_make_mflt(mf);
+	vdl2_make_sync(sw);
+	vdl2_make_softmap(soft);
+	memcpy(c_tab.mflt, mf, sizeof mf);
+	memcpy(c_tab.sync, sw, sizeof sw);
+	for (int b = 0; b < 3; b++)
+		memcpy(c_tab.soft[b], soft[b], sizeof soft[b]);
+	unsigned s = 0x4D4B;
+	for (int i = 0; i < VDL2_SCR_WORDS * 32; i++) {
+		unsigned b = (s ^ (s >> 14)) & 1u;
+		s = (s << 1) | b;
+		c_tab.scr[i >> 5] |= b << (i & 31);
+	}
+	static const unsigned char hc[25] = { 0x06, 0x07, 0x09, 0x0a, 0x0b, 0x0c, 0x0e, 0x0f, 0x11, 0x13, 0x15, 0x16, 0x18,
+		0x19, 0x1a, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f, 0x10, 0x08, 0x04, 0x02, 0x01
+	};
+	memcpy(c_tab.hcol, hc, sizeof hc);
+}
+
+/* Demodulate `ndumps` decimated samples in tiles of `tile_dumps` (<= 2688).  Record buffers
+   are caller-owned; counts come back through n_*.  Returns 0. */
+extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int chn, int Fr, Vdl2BlockRec * blocks, unsigned cap_blocks,
+			  unsigned *n_blocks, Vdl2StepRec * steps, unsigned cap_steps, unsigned *n_steps, Vdl2SyncRec * syncs,
+			  unsigned cap_syncs, unsigned *n_syncs, Vdl2SymRec * syms, unsigned cap_syms, unsigned *n_syms)
+{
+	build_tables();
+	std::vector < unsigned char >curblk(2048, 0);
+	unsigned outq_count = 0, dropped = 0;
+	Vdl2KParams kp;
+	memset(&kp, 0, sizeof kp);
+	kp.nch = 1;
+	kp.curblk = curblk.data();
+	kp.outq = blocks;
+	kp.outq_count = &outq_count;
+	kp.outq_cap = cap_blocks;
+	kp.dropped = &dropped;
+	kp.taps = VDL2_TAP_STEPS_BIT | VDL2_TAP_SYNCS_BIT | VDL2_TAP_SYMS_BIT;
+	kp.tap_steps = steps;
+	kp.tap_syncs = syncs;
+	kp.tap_syms = syms;
+	kp.cap_steps = cap_steps;
+	kp.cap_syncs = cap_syncs;
+	kp.cap_syms = cap_syms;
+
+	std::vector < float2 > sd(VDL2_HIST + VDL2_TILE_DUMPS);
+	float phb[96] = { 0 }, hv[32] = { 0 };
+	for (int i = 0; i < VDL2_HIST; i++)
+		sd[i] = make_float2(0.f, 0.f);
+	vdl2::ChanRegs R;
+	memset(&R, 0, sizeof R);
+	R.perr = 100.f;
+	R.state = VDL2_ST_WSYNC;
+	R.sync_dump = -1;
+	TileJob job;
+	for (long base = 0; base < ndumps; base += tile_dumps) {
+		const int nd = (int)((ndumps - base) < tile_dumps ? (ndumps - base) : tile_dumps);
+		for (int i = 0; i < nd; i++)
+			sd[VDL2_HIST + i] = make_float2(dumps[2 * (base + i)], dumps[2 * (base + i) + 1]);
+		job.kp = &kp;
+		job.ch = 0;
+		job.chn = chn;
+		job.Fr = Fr;
+		job.nd = nd;
+		job.dump_base = base;
+		job.sd = sd.data();
+		job.phb = phb;
+		job.hv = hv;
+		job.R0 = R;
+		run_warp(&job);
+		for (int l = 1; l < 32; l++)
+			if (!same_regs(job.Rout[l], job.Rout[0])) {
+				fprintf(stderr, "emul: lane %d state diverged from lane 0 at tile base %ld\n", l, base);
+				return 2;
+			}
+		R = job.Rout[0];
+		for (int i = 0; i < VDL2_HIST; i++)
+			sd[i] = sd[nd + i];
+	}
+	*n_blocks = outq_count;
+	*n_steps = R.n_steps;
+	*n_syncs = R.n_syncs;
+	*n_syms = R.n_syms;
+	return 0;
+}

@@ -1,0 +1,26 @@
+"""Quick device-resident throughput probe (noise input = idle-mode worst case)."""
+import sys, time
+import torch
+sys.path.insert(0, ".")
+from vdlm2dec_b200.api import Vdl2Gpu
+
+nch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+ns = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 21
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+cps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+ns = ns // 2000 * 2000
+nstreams = nch // cps
+x = torch.randint(0, 256, (nstreams, ns * 2), dtype=torch.uint8, device="cuda")
+# gaussian-ish noise around 127: sum of 4 uniforms
+x = ((x.float() + torch.randint(0, 256, x.shape, device="cuda").float()) * 0.0625 + 111.0).to(torch.uint8)
+fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+chans = [(c, 136_975_000, fos[c % len(fos)]) for c in range(nch)]
+g = Vdl2Gpu(chans, ch_per_stream=cps, max_samples=ns)
+torch.cuda.synchronize()
+for r in range(reps):
+    g.process_device(x.data_ptr(), ns, x.stride(0))
+    g.sync()
+    st = g.stats()
+    ms = st["last_kernel_ms"]
+    print(f"rep {r}: {ms:.3f} ms  {nch*ns/ms/1e3:.1f} Msamples/s  {nstreams*ns*2/ms/1e6:.1f} GB/s  grid {st['grid']} smem {st['smem_bytes']}")
+print("blocks", len(g.drain_blocks()))

@@ -8,6 +8,7 @@
 #ifndef VDL2_COMMON_H
 #define VDL2_COMMON_H
 #include <stdint.h>
+#include <vector_types.h>
 
 #define VDL2_DUMPS_PER_ROW 84
 #define VDL2_ROWS_PER_TILE 32	/* one row per lane */
