@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- IQ Msamples/s of multi-channel VDL2 D8PSK demodulation on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is ONE pass of the fused front-end kernel over one batch: `--channels` (1024) independent
+2 Msps cu8 IQ streams x `--samples` (2^22) samples per GPU, synthetic (AWGN + seeded valid VDL2
+bursts), resident in HBM before the timed region.  Channels shard across GPUs with no data-path
+collective (weak scaling: 1024 channels per GPU); torch.distributed is used only for the
+barrier and the max-over-ranks of the device time.
+
+One JSON line on stdout (rank 0).  `value` = channel-samples/s with inputs resident in HBM,
+`e2e` = the same through the C ABI with pinned HOST buffers (H2D + block drain inside the timed
+region), `roofline` = algorithmic HBM bytes / CUDA-event kernel time against the measured copy
+bandwidth, `cpu_baseline` = the reference's own d8psk.c path (oracle/_ref) on the host cores.
+`--impl reference` times only that CPU path, on all host threads, same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "IQ Msamples/s (multi-ch D8PSK demod)"
+FS = 2_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=1024, help="channels per GPU (BASELINE config 3: 1024)")
+    ap.add_argument("--samples", type=int, default=1 << 22, help="IQ samples per channel per step")
+    ap.add_argument("--ch-per-stream", type=int, default=1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def _pick_cpu_kind():
+    """oracle/_ref (the reference's own d8psk.c, -Ofast) when it loads and runs here, else the port."""
+    from oracle import pyoracle
+    for kind in ("ref_native", "ref_fast"):
+        if not pyoracle.available(kind):
+            continue
+        probe = ("import sys; sys.path.insert(0, %r); import numpy as np; from oracle import pyoracle; "
+                 "pyoracle.time_cu8(%r, np.full(40000, 127, np.uint8), 1)") % (ROOT, kind)
+        if subprocess.run([sys.executable, "-c", probe], capture_output=True).returncode == 0:  # SIGILL-safe
+            return kind, "reference"
+    if not pyoracle.available("port"):
+        pyoracle.build("port")
+    return "port", "port"
+
+
+def cpu_throughput(iq_rows, fos, target_cpu_seconds: float, threads: int | None = None):
+    """Reference CPU path on `threads` host threads, one private channel each (throughput mode of
+    BASELINE.md section 3): returns (Msamples/s, threads, kind, sample description)."""
+    import numpy as np
+    from oracle import pyoracle
+    kind, label = _pick_cpu_kind()
+    threads = threads or os.cpu_count() or 1
+    n = iq_rows.shape[1] // 2
+    # calibrate one pass on one thread, then size reps so total CPU work ~ target_seconds
+    t1 = pyoracle.time_cu8(kind, iq_rows[0], 1, Fo=fos[0])
+    reps = max(1, min(256, int(round(target_cpu_seconds / threads / max(t1, 1e-6)))))
+    res = [0.0] * threads
+
+    def work(i):
+        r = i % iq_rows.shape[0]
+        res[i] = pyoracle.time_cu8(kind, iq_rows[r], reps, Fo=fos[r])
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = time.perf_counter() - t0
+    total = threads * reps * n
+    lib = {"ref_native": "reference d8psk.c -Ofast -march=native", "ref_fast": "reference d8psk.c -Ofast -march=x86-64-v3",
+           "port": "oracle port -O2"}[kind]
+    desc = f"{threads} threads x {reps} passes x {n} samples of one channel each ({lib}); single-thread {n / t1 / 1e6:.1f} Msamples/s"
+    return total / wall / 1e6, threads, label, desc
+
+
+def host_workload(nrows: int, nsamples: int, seed: int):
+    """Small host-side (numpy) version of the workload for the CPU-only reference arm."""
+    import numpy as np
+    from vdlm2dec_b200 import synth
+    fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+    rows = []
+    for c in range(nrows):
+        spec = synth.standard_channel(seed=seed + c, nsamples=nsamples, Fo=fos[c % len(fos)], period=int(0.4 * FS),
+                                      payload_bytes=(30, 600))
+        rows.append(synth.render_channel(spec, nsamples))
+    return np.stack(rows), [fos[c % len(fos)] for c in range(nrows)]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = min(args.samples, 1 << 21)
+    iq, fos = host_workload(2, n, seed=100)
+    vals = []
+    kind = desc = None
+    threads = os.cpu_count() or 1
+    for s in range(args.warmup + args.steps):
+        v, threads, kind, desc = cpu_throughput(iq, fos, target_cpu_seconds=1.0 * threads)  # ~1 s wall per step
+        if s >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.channels} ch/GPU x {args.samples} samples, 2 Msps cu8 IQ, 1 ch/stream (BASELINE config 3); "
+                               f"CPU arm runs a bounded sample of it", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vdlm2dec_b200.api import Vdl2Gpu
+    from vdlm2dec_b200.synth_torch import make_device_workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    nch, ns = args.channels, args.samples // 2000 * 2000
+    cps = args.ch_per_stream
+    nstreams = nch // cps
+    t_gen = time.time()
+    x, fos, nbursts = make_device_workload(nstreams, ns, seed=1000 + 17 * rank, device=dev)
+    if cps > 1:  # shared streams: channel c listens at its own Fo on stream c // cps
+        allfo = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+        chans = [(c, 136_000_000 + allfo[c % cps], allfo[c % cps] if (c % cps) else fos[c // cps]) for c in range(nch)]
+    else:
+        chans = [(c + rank * nch, 136_975_000, fos[c]) for c in range(nch)]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    g = Vdl2Gpu(chans, ch_per_stream=cps, device=local_rank, max_samples=ns,
+                max_blocks=(args.steps + 4) * max(nbursts, 64) * cps + 4096)
+    stream = torch.cuda.ExternalStream(g.cuda_stream, device=dev)
+
+    def step():
+        g.process_device(x.data_ptr(), ns, x.stride(0))
+
+    # ---- warm-up (also validates: every placed burst must come back as a block)
+    blocks_seen = 0
+    for _ in range(args.warmup):
+        step()
+        g.sync()
+        blocks_seen = len(g.drain_blocks())
+    # ---- timed region: K launches, CUDA events on the launching stream, barrier + sync both sides
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = g.stats()["kernel_launches"]
+    w0 = time.time()
+    e0.record(stream)
+    kernel_ms = []
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    w1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(w0, w1)
+    launches = g.stats()["kernel_launches"] - launches0
+    blocks_timed = len(g.drain_blocks())
+    # per-launch kernel time (events recorded by the library around the kernel on its stream)
+    for _ in range(3):
+        step()
+        g.sync()
+        kernel_ms.append(g.stats()["last_kernel_ms"])
+        g.drain_blocks()
+    kms = sum(kernel_ms) / len(kernel_ms)
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    units = nch * ns * args.steps * world  # channel-samples over all ranks
+    value = units / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + drain inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((nstreams, 2 * ns), dtype=torch.uint8, pin_memory=True)
+        hx.copy_(x)
+        torch.cuda.synchronize()
+        nrep = max(2, min(args.steps, 4))
+        g.process_ptr(hx.data_ptr(), ns, hx.stride(0))
+        g.drain_blocks()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(nrep):
+            g.process_ptr(hx.data_ptr(), ns, hx.stride(0))  # returns after the kernel finished
+            d2h += g.drain_blocks().nbytes + 32
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nch * ns * nrep * world / float(tt.item()) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep}
+        del hx
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the (only) kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = nstreams * ns * 2  # 2 B per cu8 IQ sample per stream; output bytes are negligible
+    kms_region = ms_total / args.steps  # rank 0, CUDA events on the launching stream over the timed region
+    achieved = alg_bytes / (kms_region * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("channels") == nch and tr.get("ch_per_stream") == cps:
+            traffic = tr["dram_bytes_per_sample_stream"] * nstreams * ns
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                "kernel": "vdl2_frontend_kernel", "kernel_ms": kms_region, "kernel_ms_isolated": kms, "algorithmic_bytes_per_launch": alg_bytes}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        nrows = 4
+        sub = x[:nrows, : 2 * min(ns, 1 << 21)].cpu().numpy()
+        v, cores, kind, desc = cpu_throughput(sub, fos[:nrows], args.cpu_seconds)
+        cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{nch} channels/GPU x {ns} samples, 2 Msps cu8 IQ, {cps} ch/stream (BASELINE config 3; "
+                               f"config 4 = the same per GPU at N=8)", "channels_per_gpu": nch, "samples_per_channel": ns,
+                   "bytes_per_step_per_gpu": alg_bytes, "l2": "input per step (8 GiB at defaults) >> 126 MB L2; no flush needed",
+                   "bursts_per_step_per_gpu": nbursts, "blocks_decoded_per_step": blocks_timed // max(1, args.steps) if blocks_timed else blocks_seen,
+                   "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+"""Host build + ctypes front end of the warp emulator (TEST INFRASTRUCTURE, see vdl2_emul.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.pyoracle import BLOCK_DT, STEP_DT, SYM_DT, SYNC_DT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libvdl2emul.so")
+_lib = None
+
+
+def build():
+    src = os.path.join(HERE, "emul_main.cpp")
+    deps = [src, os.path.join(HERE, "vdl2_emul.h")] + [os.path.join(ROOT, "vdlm2dec_b200", "csrc", f)
+                                                        for f in ("vdl2_demod.cuh", "vdl2_common.h", "vdl2_tables.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    cuda_inc = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", f"-I{cuda_inc}",
+                    f"-I{os.path.join(ROOT, 'vdlm2dec_b200', 'csrc')}", f"-I{HERE}", "-o", LIB, src], check=True)
+    return LIB
+
+
+def demod(dumps: np.ndarray, tile_dumps: int = 2688, chn: int = 0, Fr: int = 136_975_000):
+    """Run the kernel's phase 2 source on the host over a decimated stream; returns (blocks, steps, syncs, syms)."""
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    d = np.ascontiguousarray(dumps.astype(np.complex64)).view(np.float32)
+    n = len(dumps)
+    blocks = np.zeros(256, BLOCK_DT)
+    steps = np.zeros(n // 2 + 64, STEP_DT)
+    syncs = np.zeros(1024, SYNC_DT)
+    syms = np.zeros(n // 8 + 64, SYM_DT)
+    nb, nst, nsy, nsm = C.c_uint(0), C.c_uint(0), C.c_uint(0), C.c_uint(0)
+    rc = _lib.emul_demod(d.ctypes.data_as(C.c_void_p), C.c_long(n), int(tile_dumps), chn, Fr,
+                         blocks.ctypes.data_as(C.c_void_p), len(blocks), C.byref(nb),
+                         steps.ctypes.data_as(C.c_void_p), len(steps), C.byref(nst),
+                         syncs.ctypes.data_as(C.c_void_p), len(syncs), C.byref(nsy),
+                         syms.ctypes.data_as(C.c_void_p), len(syms), C.byref(nsm))
+    if rc:
+        raise RuntimeError(f"emul_demod failed ({rc})")
+    return blocks[:nb.value], steps[:nst.value], syncs[:nsy.value], syms[:nsm.value]

@@ -1,0 +1,49 @@
+"""Channel sharding across the GPUs of one box.
+
+The path has no exchange step: channels (with the stream they are demodulated from) are
+independent, so stream s lives on GPU `s mod N`, every GPU runs the same kernel on its own
+streams, and the host merges the completed blocks.  torch.distributed is plumbing only
+(barrier, max-over-ranks of the device time, gathering the blocks); no NCCL call sits on
+the data path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_streams(total_streams: int, rank: int, world: int) -> list[int]:
+    """Global stream indices owned by `rank`: s mod world == rank."""
+    return list(range(rank, total_streams, world))
+
+
+def shard_channels(total_streams: int, ch_per_stream: int, rank: int, world: int) -> list[int]:
+    """Global channel numbers owned by `rank` (channels follow their stream)."""
+    return [s * ch_per_stream + k for s in shard_streams(total_streams, rank, world) for k in range(ch_per_stream)]
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def merge_blocks(per_rank_blocks: list[np.ndarray]) -> np.ndarray:
+    """Union of the ranks' completed blocks in the order one GPU would have produced them
+    (oldest trigger first, then channel number)."""
+    allb = np.concatenate([b for b in per_rank_blocks if len(b)]) if any(len(b) for b in per_rank_blocks) else per_rank_blocks[0]
+    order = np.lexsort((allb["chn"], allb["sync_dump"]))
+    return allb[order]
+
+
+def gather_blocks(blocks: np.ndarray) -> np.ndarray | None:
+    """all ranks -> rank 0 (returns None elsewhere); single process: identity."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return merge_blocks([blocks])
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(blocks, out, dst=0)
+    return merge_blocks(out) if dist.get_rank() == 0 else None
