@@ -69,10 +69,21 @@ def compare_channel(o: Oracle, g_blocks, g_syncs=None, g_syms=None, g_dumps=None
         if len(osy):
             assert np.array_equal(osy["dump"], g_syms["dump"]), "symbol positions differ"
             rep["sym_D_err"] = float(wrap_diff(osy["D"], g_syms["D"]).max())
-            rep["gi_flips"] = int((osy["gi"] != g_syms["gi"]).sum())
+            flips = osy["gi"] != g_syms["gi"]
+            rep["gi_flips"] = int(flips.sum())
             assert rep["sym_D_err"] < D_TOL, f"soft symbol deviates {rep['sym_D_err']:.3e} rad"
-            assert rep["gi_flips"] == 0, f"{rep['gi_flips']} Gray index flips"
-            assert np.array_equal(osy["v"].view(np.uint32), g_syms["v"].view(np.uint32)), "soft bits differ"
+            # The table index is roundf(128*D/pi+128) (d8psk.c:213): a 1e-6 rad difference in D moves a
+            # symbol sitting on a rounding boundary to the NEIGHBOURING entry.  That is allowed only
+            # there (both D within tolerance of the same boundary) and only as a +-1 step; the hard
+            # decisions (what reaches vdlm2.c) must be identical everywhere.
+            if flips.any():
+                assert np.abs(osy["gi"][flips] - g_syms["gi"][flips]).max() == 1, "Gray index differs by more than one step"
+                x = 128.0 * osy["D"][flips].astype(np.float64) / np.pi + 128.0
+                assert np.abs(np.abs(x - np.floor(x)) - 0.5).max() < 128 / np.pi * D_TOL, "index flip away from a rounding boundary"
+                assert rep["gi_flips"] <= max(1, len(osy) // 500), f"{rep['gi_flips']} Gray index flips in {len(osy)} symbols"
+            same = ~flips
+            assert np.array_equal(osy["v"][same].view(np.uint32), g_syms["v"][same].view(np.uint32)), "soft bits differ"
+            assert np.array_equal(osy["v"] > 0.5, g_syms["v"] > 0.5), "hard bit decisions differ"
     if g_steps is not None:
         ost = o.steps
         if ndump_limit is not None:
