@@ -334,3 +334,43 @@ def standard_channel(seed: int, nsamples: int, Fo: int, fs: int = 2_000_000, per
         gap = float(rng.uniform(0.2, 1.0)) * (period if period else 40000)
         t += dur + gap
     return ChannelSpec(Fo, bursts, noise_sigma=noise_sigma, seed=seed + 7919)
+
+
+# ----------------------------------------------------------------------------- ACARS over AVLC
+def _rev(v: int, n: int) -> int:
+    return int(f"{v:0{n}b}"[::-1], 2)
+
+
+def avlc_addr(addr27: int, bit1: int, last: bool) -> bytes:
+    """Inverse of icaoaddr() (out.c:426-435): 27-bit address, 7 bits per byte, bit-reversed, LSB = HDLC extension."""
+    b0 = (_rev((addr27 >> 21) & 0x3F, 6) << 2) | (bit1 << 1)
+    b1 = _rev((addr27 >> 14) & 0x7F, 7) << 1
+    b2 = _rev((addr27 >> 7) & 0x7F, 7) << 1
+    b3 = (_rev(addr27 & 0x7F, 7) << 1) | (1 if last else 0)
+    return bytes([b0, b1, b2, b3])
+
+
+def _crc_kermit(data: bytes) -> int:
+    crc = 0
+    for b in data:
+        crc ^= b
+        for _ in range(8):
+            crc = (crc >> 1) ^ 0x8408 if crc & 1 else crc >> 1
+    return crc
+
+
+def acars_frame(icao: int, reg: str, label: str, text: str, msgno: str = "M01A", flight: str = "AB1234",
+                ground: int = 0x10A0B0) -> bytes:
+    """AVLC information frame carrying one ACARS message (what outacars.c:214-331 parses):
+    dst, src (aircraft: type 1), control, ff ff 01, ACARS body with odd parity + CRC-16 + DEL.
+    Returns the payload for hdlc_bits() (FCS and flags are added there)."""
+    body = "2" + reg.rjust(7, ".")[:7] + "\x15" + label[:2] + "1" + "\x02" + msgno[:4] + flight[:6] + text + "\x03"
+    raw = bytearray()
+    for ch in body.encode("ascii"):
+        ch &= 0x7F
+        raw.append(ch | (0x80 if bin(ch).count("1") % 2 == 0 else 0))  # odd parity in bit 7
+    crc = _crc_kermit(bytes(raw))
+    raw += bytes([crc & 0xFF, crc >> 8, 0x7F])
+    dst = avlc_addr((2 << 24) | ground, 0, False)
+    src = avlc_addr((1 << 24) | (icao & 0xFFFFFF), 0, True)
+    return dst + src + bytes([0x00, 0xFF, 0xFF, 0x01]) + bytes(raw)
