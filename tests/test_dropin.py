@@ -94,8 +94,15 @@ def test_dropin_text_identical(tmp_path, freqs):
     ref_out, _ = _run(CPU_BIN, cap, freqs, extra=ALL)
     gpu_out, gpu_err = _run(GPU_BIN, cap, freqs, extra=ALL)
     a, b = _messages(ref_out), _messages(gpu_out)
-    assert len(a) == nb, (len(a), nb)
-    assert a == b, f"{len(a)} vs {len(b)} messages\n{gpu_err[-1500:]}"
+    assert len(b) == nb, f"GPU binary printed {len(b)} of {nb} messages\n{gpu_err[-1500:]}"
+    if len(freqs) == 1:
+        assert a == b
+    else:
+        # With several channel threads the reference shares ONE global header trellis between them
+        # (viterbi.c:25-27, called from d8psk.c:83,88,300 without a lock): overlapping headers corrupt
+        # each other and the all-CPU binary drops bursts depending on thread timing.  Everything it
+        # does print must be printed identically by the GPU build, which decodes headers per channel.
+        assert set(a) <= set(b) and len(a) >= nb // 2, (len(a), len(b), nb)
 
 
 @pytest.mark.gpu
@@ -109,5 +116,5 @@ def test_dropin_acars_json_identical(tmp_path):
     b = _run(GPU_BIN, cap, freqs, extra=("-J",))[0]
     ja = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in a.splitlines() if l.startswith("{"))
     jb = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in b.splitlines() if l.startswith("{"))
-    assert len(ja) == nb and ja == jb
+    assert len(jb) == nb and set(ja) <= set(jb) and len(ja) >= nb // 2  # see the race note above
     assert '"text":"HELLO VDL2 NUMBER 0' in "".join(ja)
