@@ -47,6 +47,10 @@ enum vdl2_format {
 #define VDL2_TAP_STEPS 2u	/* T2: P, err, fr of every idle (WSYNC) step */
 #define VDL2_TAP_SYNCS 4u	/* T3: trigger events */
 #define VDL2_TAP_SYMS  8u	/* T4/T5: per-symbol differential phase, Gray index, 3 soft bits */
+/* option bit in the same mask: evaluate the full 17-point sync fit at EVERY idle step like the
+   reference does (d8psk.c:259-289) instead of only where the screen says err < 4 is possible;
+   same outputs, slower; implied by VDL2_TAP_STEPS */
+#define VDL2_OPT_EXACT_IDLE 0x100u
 
 /* mirrors thread_param_t (vdlm2.h:49-52) */
 typedef struct {

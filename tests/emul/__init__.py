@@ -25,7 +25,7 @@ def build():
     return LIB
 
 
-def demod(dumps: np.ndarray, tile_dumps: int = 2688, chn: int = 0, Fr: int = 136_975_000):
+def demod(dumps: np.ndarray, tile_dumps: int = 2688, chn: int = 0, Fr: int = 136_975_000, flags: int = 0, want_steps: bool = True):
     """Run the kernel's phase 2 source on the host over a decimated stream; returns (blocks, steps, syncs, syms)."""
     global _lib
     if _lib is None:
@@ -37,9 +37,9 @@ def demod(dumps: np.ndarray, tile_dumps: int = 2688, chn: int = 0, Fr: int = 136
     syncs = np.zeros(1024, SYNC_DT)
     syms = np.zeros(n // 8 + 64, SYM_DT)
     nb, nst, nsy, nsm = C.c_uint(0), C.c_uint(0), C.c_uint(0), C.c_uint(0)
-    rc = _lib.emul_demod(d.ctypes.data_as(C.c_void_p), C.c_long(n), int(tile_dumps), chn, Fr,
+    rc = _lib.emul_demod(d.ctypes.data_as(C.c_void_p), C.c_long(n), int(tile_dumps), chn, Fr, C.c_uint(flags),
                          blocks.ctypes.data_as(C.c_void_p), len(blocks), C.byref(nb),
-                         steps.ctypes.data_as(C.c_void_p), len(steps), C.byref(nst),
+                         steps.ctypes.data_as(C.c_void_p) if want_steps else None, len(steps), C.byref(nst),
                          syncs.ctypes.data_as(C.c_void_p), len(syncs), C.byref(nsy),
                          syms.ctypes.data_as(C.c_void_p), len(syms), C.byref(nsm))
     if rc:

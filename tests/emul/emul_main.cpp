@@ -34,7 +34,9 @@ struct TileJob {
 	int ch, chn, Fr, nd;
 	long long dump_base;
 	float2 *sd;
-	float *phb, *hv;
+	vdl2::IdleScratch S;
+	float *hv;
+	int nph[32];
 	vdl2::ChanRegs R0;
 	vdl2::ChanRegs Rout[32];
 };
@@ -44,7 +46,9 @@ static void lane_main(int lane)
 {
 	TileJob *j = g_job;
 	vdl2::ChanRegs R = j->R0;
-	vdl2::demod_tile(*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->phb, j->hv, j->nd, j->dump_base);
+	int nph = 0;
+	vdl2::demod_tile(*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->S, j->hv, j->nd, j->dump_base, nph);
+	j->nph[lane] = nph;
 	j->Rout[lane] = R;
 	vw::g_done[lane] = 1;
 }
@@ -113,7 +117,7 @@ static void build_tables()
 
 /* Demodulate `ndumps` decimated samples in tiles of `tile_dumps` (<= 2688).  Record buffers
    are caller-owned; counts come back through n_*.  Returns 0. */
-extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int chn, int Fr, Vdl2BlockRec * blocks, unsigned cap_blocks,
+extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int chn, int Fr, unsigned flags, Vdl2BlockRec * blocks, unsigned cap_blocks,
 			  unsigned *n_blocks, Vdl2StepRec * steps, unsigned cap_steps, unsigned *n_steps, Vdl2SyncRec * syncs,
 			  unsigned cap_syncs, unsigned *n_syncs, Vdl2SymRec * syms, unsigned cap_syms, unsigned *n_syms)
 {
@@ -128,7 +132,8 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	kp.outq_count = &outq_count;
 	kp.outq_cap = cap_blocks;
 	kp.dropped = &dropped;
-	kp.taps = VDL2_TAP_STEPS_BIT | VDL2_TAP_SYNCS_BIT | VDL2_TAP_SYMS_BIT;
+	kp.taps = (steps ? VDL2_TAP_STEPS_BIT : 0u) | VDL2_TAP_SYNCS_BIT | VDL2_TAP_SYMS_BIT;
+	kp.flags = flags;
 	kp.tap_steps = steps;
 	kp.tap_syncs = syncs;
 	kp.tap_syms = syms;
@@ -137,7 +142,10 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	kp.cap_syms = cap_syms;
 
 	std::vector < float2 > sd(VDL2_HIST + VDL2_TILE_DUMPS);
-	float phb[96] = { 0 }, hv[32] = { 0 };
+	float hv[32] = { 0 };
+	std::vector < float >pht(VDL2_PHT_LEN, 0.f);
+	std::vector < float2 > vwin(96);
+	std::vector < unsigned short >cand(VDL2_CAND_CAP);
 	for (int i = 0; i < VDL2_HIST; i++)
 		sd[i] = make_float2(0.f, 0.f);
 	vdl2::ChanRegs R;
@@ -157,7 +165,9 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 		job.nd = nd;
 		job.dump_base = base;
 		job.sd = sd.data();
-		job.phb = phb;
+		job.S.pht = pht.data();
+		job.S.vw = vwin.data();
+		job.S.cand = cand.data();
 		job.hv = hv;
 		job.R0 = R;
 		run_warp(&job);
@@ -167,6 +177,11 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 				return 2;
 			}
 		R = job.Rout[0];
+		{
+			const int nph = job.nph[0];
+			for (int i = 0; i < VDL2_PHHIST; i++)
+				pht[i] = pht[nph + i];
+		}
 		for (int i = 0; i < VDL2_HIST; i++)
 			sd[i] = sd[nd + i];
 	}

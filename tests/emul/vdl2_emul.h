@@ -56,6 +56,9 @@ VQ unsigned ballot(bool p)
 VQ unsigned atomic_inc(unsigned *p) { return (*p)++; }
 VQ void fence() {}
 VQ int ffs(unsigned m) { return __builtin_ffs((int)m); }
+VQ int popc(unsigned m) { return __builtin_popcount(m); }
+VQ void sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
+VQ float rsqrt(float a) { return 1.0f / sqrtf(a); }
 VQ float fma(float a, float b, float c) { return fmaf(a, b, c); }
 VQ float atan2(float y, float x) { return atan2f(y, x); }
 VQ float fdiv(float a, float b) { return a / b; }

@@ -10,20 +10,22 @@ import pytest
 from oracle.pyoracle import Oracle
 from tests.parity_util import compare_channel, make_channels, run_oracle
 from vdlm2dec_b200 import synth
-from vdlm2dec_b200.api import TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
+from vdlm2dec_b200.api import OPT_EXACT_IDLE, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
 
 pytestmark = pytest.mark.gpu
-ALL_TAPS = TAP_DUMPS | TAP_STEPS | TAP_SYNCS | TAP_SYMS
+ALL_TAPS = TAP_DUMPS | TAP_STEPS | TAP_SYNCS | TAP_SYMS  # TAP_STEPS implies the exact fit at every idle step
+SCREEN_TAPS = TAP_DUMPS | TAP_SYNCS | TAP_SYMS            # production path: screened idle search
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _check_all(g, specs, iq, fmt, blocks=None, ndump_limit=None, taps=True, fs=2_000_000):
+def _check_all(g, specs, iq, fmt, blocks=None, ndump_limit=None, taps=True, fs=2_000_000, steps=True):
     blocks = g.drain_blocks() if blocks is None else blocks
     reps = []
     for c, spec in enumerate(specs):
         o = run_oracle(iq[c], spec.Fo, fmt=fmt, chn=c, fs=fs)
         if taps:
-            gd, gs, gy, gt = g.read_dumps(c), g.read_syncs(c), g.read_syms(c), g.read_steps(c)
+            gd, gs, gy = g.read_dumps(c), g.read_syncs(c), g.read_syms(c)
+            gt = g.read_steps(c) if steps else None
             lim = len(gd) if ndump_limit is None else ndump_limit
             reps.append(compare_channel(o, blocks[blocks["chn"] == c], gs, gy, gd, gt, ndump_limit=lim))
         else:
@@ -31,13 +33,15 @@ def _check_all(g, specs, iq, fmt, blocks=None, ndump_limit=None, taps=True, fs=2
     return reps
 
 
+@pytest.mark.parametrize("screen", [True, False])
 @pytest.mark.parametrize("fmt", ["cu8", "cs8", "cf32"])
-def test_parity_formats(fmt):
+def test_parity_formats(fmt, screen):
     nch, n = 6, 1_200_000
     specs, iq = make_channels(nch, n, seed=3, fmt=fmt)
-    g = Vdl2Gpu([(c, 136_975_000, specs[c].Fo) for c in range(nch)], fmt=fmt, taps=ALL_TAPS, max_samples=n)
+    g = Vdl2Gpu([(c, 136_975_000, specs[c].Fo) for c in range(nch)], fmt=fmt, taps=SCREEN_TAPS if screen else ALL_TAPS,
+                max_samples=n)
     g.process(iq)
-    reps = _check_all(g, specs, iq, fmt)
+    reps = _check_all(g, specs, iq, fmt, steps=not screen)
     assert sum(r["blocks"][0] for r in reps) >= nch  # the vectors do contain bursts
     assert g.stats()["kernel_launches"] == 1
 
@@ -149,6 +153,28 @@ def test_golden_fixture_gpu():
     assert np.array_equal(syms["gi"], gl["sym_gi"])
     assert np.abs(syms["D"] - gl["sym_D"]).max() < 1e-5
     assert np.array_equal(syncs["dump"], np.frombuffer(gl["syncs"].tobytes(), dtype=syncs.dtype)["dump"])
+
+
+@pytest.mark.parametrize("amp,sigma", [((6.0, 9.0), 8.0), ((10.0, 16.0), 8.0), ((40.0, 60.0), 2.0)])
+def test_screened_idle_search_equals_exact(amp, sigma):
+    """The screen only skips fits that provably cannot trigger: weak, marginal and very clean signals
+    (false triggers on stale preambles included) must give identical events with and without it."""
+    nch, n = 8, 1_600_000
+    specs, iq = make_channels(nch, n, seed=21, amp=amp, noise_sigma=sigma)
+    chans = [(c, 136_975_000, specs[c].Fo) for c in range(nch)]
+    a = Vdl2Gpu(chans, taps=TAP_SYNCS | TAP_SYMS, max_samples=n)
+    b = Vdl2Gpu(chans, taps=TAP_SYNCS | TAP_SYMS | OPT_EXACT_IDLE, max_samples=n)
+    a.process(iq)
+    b.process(iq)
+    ba, bb = a.drain_blocks(), b.drain_blocks()
+    assert ba.tobytes() == bb.tobytes()
+    nsync = 0
+    for c in range(nch):
+        sa, sb = a.read_syncs(c), b.read_syncs(c)
+        assert sa.tobytes() == sb.tobytes() and a.read_syms(c).tobytes() == b.read_syms(c).tobytes()
+        nsync += len(sa)
+    assert nsync >= nch
+    _check_all(a, specs, iq, "cu8", blocks=ba, taps=False, ndump_limit=n // 2000 * 84)
 
 
 def test_full_width_1024_channels_properties():

@@ -18,6 +18,7 @@
 #define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
 #define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
 
+#define VDL2_FLAG_NO_SCREEN 1u	/* debug: run the exact 17-point fit at every idle step */
 #define VDL2_TAP_DUMPS_BIT 1u
 #define VDL2_TAP_STEPS_BIT 2u
 #define VDL2_TAP_SYNCS_BIT 4u
@@ -87,6 +88,7 @@ struct Vdl2KParams {
 	unsigned outq_cap;
 	unsigned *dropped;
 	unsigned taps;
+	unsigned flags;		/* VDL2_FLAG_* */
 	float2 *tap_dumps;	/* [nch][cap_dumps] */
 	Vdl2StepRec *tap_steps;	/* [nch][cap_steps] */
 	Vdl2SyncRec *tap_syncs;	/* [nch][cap_syncs] */

@@ -43,8 +43,11 @@ VQ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 VQ unsigned atomic_inc(unsigned *p) { return atomicAdd(p, 1u); }
 VQ void fence() { __threadfence(); }
 VQ int ffs(unsigned m) { return __ffs(m); }
+VQ int popc(unsigned m) { return __popc(m); }
 VQ float fma(float a, float b, float c) { return fmaf(a, b, c); }
 VQ float atan2(float y, float x) { return atan2f(y, x); }
+VQ void sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
+VQ float rsqrt(float a) { return rsqrtf(a); }
 VQ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
 VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -252,7 +255,8 @@ VQ unsigned header_decode(const float *hv)
 /* ---------------------------------------------------------------------------------------
  * demod_tile: consume dumps [0, nd) of one tile.
  *   sd   : shared, float2[16 + nd], sd[16 + i] = dump i, sd[0..15] = history
- *   phb  : shared, float[96]; phb[0..63] = the 64 previous idle-mode phases (oldest first)
+ *   S    : shared scratch of the idle search; S.pht[0..63] = the 64 previous idle-mode phases (oldest
+ *          first); on return nph phases were appended (the new history is S.pht[nph .. nph+63])
  *   hv   : shared, float[28]; header soft bits collected so far
  *   st   : the channel's state in HBM (read at entry, written back at exit by the caller
  *          through the ChanRegs copy below)
@@ -295,111 +299,269 @@ VQ void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long
 	vw::sync();
 }
 
-VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, float *phb, float *hv,
-		   int nd, long long dump_base)
+/* scratch of the idle-mode search (shared memory; the kernel lends it the idle TMA stages) */
+#define VDL2_PHT_LEN (VDL2_PHHIST + VDL2_TILE_DUMPS / 2 + 32)
+#define VDL2_CAND_CAP 192
+struct IdleScratch {
+	float *pht;		/* [VDL2_PHT_LEN]: pht[0..63] = the 64 phases before the tile, then one per idle step */
+	float2 *vw;		/* [96]: differential phasors v_t = z_t conj(z_{t-4}), sliding window */
+	unsigned short *cand;	/* [VDL2_CAND_CAP]: steps that passed the screen */
+};
+
+/* filter only (no phase): 17 taps, steady-state tap phase */
+VQ void filt17(const float2 * sd, int d, const float *m, float &sr, float &si)
+{
+	sr = 0.f;
+	si = 0.f;
+#pragma unroll
+	for (int j = 0; j < 17; j++) {
+		const float2 x = sd[d + j];
+		sr = vw::fma(x.x, m[j], sr);
+		si = vw::fma(x.y, m[j], si);
+	}
+}
+
+VQ float2 cmul_conj(float2 a, float2 b)
+{				/* a * conj(b) */
+	return make_float2(vw::fma(a.x, b.x, a.y * b.y), vw::fma(a.y, b.x, -(a.x * b.y)));
+}
+
+/* ---------------------------------------------------------------------------------------
+ * idle_run: all idle-mode steps from `pos` to the end of the tile (or to the first trigger).
+ *
+ * The reference evaluates the full 17-point fit at every step (d8psk.c:259-289) although the
+ * trigger needs it only around residuals below 4.0.  Here every step still gets its exact
+ * phase P (the Ph ring must stay exact), but the fit runs only where a cheap NECESSARY
+ * condition for err < 4 holds:
+ *   with u_l = exp(i(Pr_l - Pr_{l-1})) = z_l conj(z_{l-1}) exp(-i(SW_l - SW_{l-1})), z = exp(iP),
+ *   err = sum e_l^2 < 4  =>  |sum_{l=1..16} u_l| >= 16 - (lambda_max/2) err > 8.07
+ *   (lambda_max = 2 - 2cos(16pi/17) of the 17-node path Laplacian; DESIGN.md "idle screen").
+ * SW_l - SW_{l-1} = (2 q_l + 1) pi/8 with q_l the unique word, so the sum is a 16-tap
+ * correlation of the differential phasors with multiples of pi/4: adds and swaps only.
+ * Steps passing |sum|^2 >= 62 (|sum| >= 7.87, margin for fp32) are "candidates"; the exact
+ * fit runs lane-parallel over the candidate list; the first candidate whose exact err < 4
+ * switches the rest of the run to the exact lane-per-step search, two steps early so that
+ * p2err/perr/pfr are the reference's values at the trigger.  Everything before it provably
+ * cannot trigger.  The last two steps of a run are always fitted (state for the next tile).
+ * ------------------------------------------------------------------------------------- */
+#define VDL2_SCREEN_THR2 62.0f
+
+VQ void idle_trigger(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, long long dump_base, int dT, float eT,
+		     float pT, float p2T, float fT)
+{				/* d8psk.c:292-308 */
+	R.state = VDL2_ST_GETHEAD;
+	R.symidx = 0;
+	R.df = fT;
+	R.ppm = (float)((double)vw::fmul(10500.0f, R.df) / (2.0 * VDL2_PI_D * (double)Fr) * 1e6);
+	const float num = vw::fmul(4.0f, vw::fadd(vw::fsub(p2T, vw::fmul(4.0f, pT)), vw::fmul(3.0f, eT)));
+	const float den = vw::fadd(vw::fsub(p2T, vw::fmul(2.0f, pT)), eT);
+	const float of = vw::fdiv(num, den);
+	int nclk = (int)roundf(of);
+	nclk = nclk < 0 ? 0 : (nclk > 64 ? 64 : nclk);	/* of is in [4,12] for finite input */
+	R.clk = nclk;
+	R.P1 = filt_phase_any(sd, dT, nclk);
+	R.perr = R.p2err = 500.f;
+	R.sync_dump = dump_base + dT;
+	if ((kp.taps & VDL2_TAP_SYNCS_BIT)) {
+		if (vw::lane() == 0 && R.n_syncs < kp.cap_syncs) {
+			Vdl2SyncRec s;
+			s.dump = R.sync_dump;
+			s.clk = nclk;
+			s.df = R.df;
+			s.ppm = R.ppm;
+			s.P1 = R.P1;
+			kp.tap_syncs[(size_t) ch * kp.cap_syncs + R.n_syncs] = s;
+		}
+		R.n_syncs++;
+	}
+}
+
+VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, const IdleScratch & S, int nd,
+		 long long dump_base, int &pos, int &nph)
+{
+	const int lane = vw::lane();
+	if (R.clk >= 8)
+		R.clk &= 7;	/* unreachable for finite input (clk < 8 whenever the burst clock was sane) */
+	const int c4 = R.clk >= 4;
+	const int p0 = pos + (c4 ? 0 : 1);	/* dump of the first step: a step every 2nd dump (d8psk.c:248-250) */
+	const int r = c4 ? R.clk - 4 : R.clk;	/* tap phase of every step of the run */
+	if (p0 >= nd) {
+		R.clk += 4 * (nd - pos);
+		pos = nd;
+		return;
+	}
+	const int N = ((nd - 1 - p0) >> 1) + 1;	/* steps in this run */
+	float *ph = S.pht + nph;	/* ph[0..63] = history, ph[64 + k] = phase of step k */
+	float m[17];
+#pragma unroll
+	for (int j = 0; j < 17; j++)
+		m[j] = c_tab.mflt[r + 4 * j];	/* r + 64 <= 67: zero padded */
+
+	const bool exact_only = (kp.taps & VDL2_TAP_STEPS_BIT) || (kp.flags & VDL2_FLAG_NO_SCREEN) || !(R.perr >= 4.0f) || N < 8;
+
+	/* ---- pass A: exact phase of every step; screen ---- */
+	int ncand = 0;
+	bool overflow = false;
+	float2 zlast = make_float2(1.f, 0.f);
+	if (!exact_only) {
+		float2 zA, zB;
+		vw::sincos(ph[lane], zA.y, zA.x);
+		vw::sincos(ph[32 + lane], zB.y, zB.x);
+		const float2 a4 = make_float2(vw::shfl_up(zA.x, 4), vw::shfl_up(zA.y, 4));
+		const float2 b4u = make_float2(vw::shfl_up(zB.x, 4), vw::shfl_up(zB.y, 4));
+		const float2 b4w = make_float2(vw::shfl(zA.x, (lane + 28) & 31), vw::shfl(zA.y, (lane + 28) & 31));
+		S.vw[lane] = cmul_conj(zA, a4);	/* entries 0..3 are never read */
+		S.vw[32 + lane] = cmul_conj(zB, lane >= 4 ? b4u : b4w);
+		zlast = zB;
+		vw::sync();
+	}
+	for (int b0 = 0; b0 < N; b0 += 32) {
+		const int k = b0 + lane;
+		float sr = 1.f, si = 0.f;
+		if (k < N)
+			filt17(sd, p0 + 2 * k, m, sr, si);
+		const float P = vw::atan2(si, sr);
+		if (k < N)
+			ph[VDL2_PHHIST + k] = P;
+		if (!exact_only) {
+			const float mag2 = vw::fma(sr, sr, si * si);
+			const bool ok = (mag2 > 1e-30f) && (mag2 < 1e30f);
+			const float rn = vw::rsqrt(ok ? mag2 : 1.f);
+			const float2 z = make_float2(sr * rn, si * rn);
+			const float2 z4u = make_float2(vw::shfl_up(z.x, 4), vw::shfl_up(z.y, 4));
+			const float2 z4w = make_float2(vw::shfl(zlast.x, (lane + 28) & 31), vw::shfl(zlast.y, (lane + 28) & 31));
+			S.vw[64 + lane] = cmul_conj(z, lane >= 4 ? z4u : z4w);
+			zlast = z;
+			vw::sync();
+			/* correlation with the unique word: q = 0,3,2,4,0,1,6,4,1,7,2,5,6,5,7,3 (multiples of pi/4) */
+			float2 A0 = make_float2(0.f, 0.f), A2 = A0, B0 = A0, B2 = A0;
+#define VDL2_ACC(L, Q) { const float2 w = S.vw[lane + 4 * (L)]; \
+	if ((Q) == 0) { A0.x += w.x; A0.y += w.y; } else if ((Q) == 4) { A0.x -= w.x; A0.y -= w.y; } \
+	else if ((Q) == 2) { A2.x += w.x; A2.y += w.y; } else if ((Q) == 6) { A2.x -= w.x; A2.y -= w.y; } \
+	else if ((Q) == 1) { B0.x += w.x; B0.y += w.y; } else if ((Q) == 5) { B0.x -= w.x; B0.y -= w.y; } \
+	else if ((Q) == 3) { B2.x += w.x; B2.y += w.y; } else { B2.x -= w.x; B2.y -= w.y; } }
+			VDL2_ACC(1, 0) VDL2_ACC(2, 3) VDL2_ACC(3, 2) VDL2_ACC(4, 4) VDL2_ACC(5, 0) VDL2_ACC(6, 1) VDL2_ACC(7, 6) VDL2_ACC(8, 4)
+			VDL2_ACC(9, 1) VDL2_ACC(10, 7) VDL2_ACC(11, 2) VDL2_ACC(12, 5) VDL2_ACC(13, 6) VDL2_ACC(14, 5) VDL2_ACC(15, 7) VDL2_ACC(16, 3)
+#undef VDL2_ACC
+			/* C = A0 - i A2 + exp(-i pi/4) (B0 - i B2) */
+			const float cx = A0.x + A2.y, cy = A0.y - A2.x;
+			const float dx = B0.x + B2.y, dy = B0.y - B2.x;
+			const float sx = cx + 0.70710678f * (dx + dy), sy = cy + 0.70710678f * (dy - dx);
+			const float c2 = vw::fma(sx, sx, sy * sy);
+			const bool cand = (k < N) && (!ok || !(c2 < VDL2_SCREEN_THR2) || k >= N - 2);
+			const unsigned cm = vw::ballot(cand);
+			const int slot = ncand + vw::popc(cm & ((1u << lane) - 1u));
+			if (cand && slot < VDL2_CAND_CAP)
+				S.cand[slot] = (unsigned short)k;
+			ncand += vw::popc(cm);
+			if (ncand > VDL2_CAND_CAP)
+				overflow = true;
+			/* slide the window by 32 steps */
+			const float2 w1 = S.vw[32 + lane], w2 = S.vw[64 + lane];
+			vw::sync();
+			S.vw[lane] = w1;
+			S.vw[32 + lane] = w2;
+			vw::sync();
+		}
+	}
+	vw::sync();
+
+	/* ---- pass B: exact fit of the candidates, in time order, until the first err < 4 ---- */
+	int s0 = exact_only || overflow ? 0 : -1;	/* first step of the exact search; -1: no trigger possible in this run */
+	float eN1 = 0.f, eN2 = 0.f, fN1 = 0.f;
+	if (s0 < 0) {
+		for (int c0 = 0; c0 < ncand; c0 += 32) {
+			const bool have = c0 + lane < ncand;
+			const int k = have ? (int)S.cand[c0 + lane] : 0;
+			float err, fr;
+			sync_fit(ph + k, err, fr);
+			const unsigned hm = vw::ballot(have && err < 4.0f);
+			const unsigned l1 = vw::ballot(have && k == N - 1), l2 = vw::ballot(have && k == N - 2);
+			if (l1) {
+				eN1 = vw::shfl(err, vw::ffs(l1) - 1);
+				fN1 = vw::shfl(fr, vw::ffs(l1) - 1);
+			}
+			if (l2)
+				eN2 = vw::shfl(err, vw::ffs(l2) - 1);
+			if (hm) {
+				const int first = vw::shfl(k, vw::ffs(hm) - 1);
+				s0 = first >= 2 ? first - 2 : 0;
+				break;
+			}
+		}
+	}
+	if (s0 < 0) {		/* nothing below 4.0 anywhere: the whole run is committed */
+		nph += N;
+		R.p2err = eN2;
+		R.perr = eN1;
+		R.pfr = fN1;
+		pos = p0 + 2 * (N - 1) + 1;
+		R.clk = r;
+		return;
+	}
+
+	/* ---- exact search from step s0: one lane per step, reference trigger logic ---- */
+	if (s0 > 0)
+		R.perr = R.p2err = 500.f;	/* steps s0-1, s0-2 had err >= 4: any such value gives the same decisions */
+	for (int b0 = s0; b0 < N; b0 += 32) {
+		const int nb = (N - b0) < 32 ? (N - b0) : 32;
+		const int k = b0 + lane;
+		float err, fr;
+		sync_fit(ph + (k < N ? k : 0), err, fr);
+		const float e1 = vw::shfl_up(err, 1), e2 = vw::shfl_up(err, 2), f1 = vw::shfl_up(fr, 1);
+		const float perr_l = lane >= 1 ? e1 : R.perr;
+		const float p2err_l = lane >= 2 ? e2 : (lane == 1 ? R.perr : R.p2err);
+		const float pfr_l = lane >= 1 ? f1 : R.pfr;
+		const bool trig = (lane < nb) && (perr_l < 4.0f) && (err > perr_l);
+		const unsigned tm = vw::ballot(trig);
+		const int K = tm ? vw::ffs(tm) : nb;	/* steps committed, trigger step included */
+		if ((kp.taps & VDL2_TAP_STEPS_BIT) && lane < K) {
+			const unsigned idx = R.n_steps + lane;
+			if (idx < kp.cap_steps) {
+				Vdl2StepRec s;
+				s.dump = dump_base + p0 + 2 * k;
+				s.P = ph[VDL2_PHHIST + k];
+				const bool tl = tm && lane == K - 1;
+				s.err = tl ? -1.0f : err;
+				s.fr = tl ? pfr_l : fr;
+				s.pad = 0;
+				kp.tap_steps[(size_t) ch * kp.cap_steps + idx] = s;
+			}
+		}
+		R.n_steps += (kp.taps & VDL2_TAP_STEPS_BIT) ? K : 0;
+		if (!tm) {
+			const float eL = vw::shfl(err, K - 1), fL = vw::shfl(fr, K - 1);
+			const float eP = vw::shfl(err, K >= 2 ? K - 2 : 0);
+			R.p2err = K >= 2 ? eP : R.perr;
+			R.perr = eL;
+			R.pfr = fL;
+		} else {
+			const int T = K - 1;
+			const float eT = vw::shfl(err, T), pT = vw::shfl(perr_l, T);
+			const float p2T = vw::shfl(p2err_l, T), fT = vw::shfl(pfr_l, T);
+			const int dT = p0 + 2 * (b0 + T);
+			idle_trigger(kp, ch, Fr, R, sd, dump_base, dT, eT, pT, p2T, fT);
+			nph += b0 + T + 1;	/* the Ph ring stops at the trigger step (d8psk.c:254-255) */
+			pos = dT + 1;
+			return;
+		}
+	}
+	nph += N;
+	pos = p0 + 2 * (N - 1) + 1;
+	R.clk = r;
+}
+
+VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, const IdleScratch & S, float *hv,
+		   int nd, long long dump_base, int &nph)
 {
 	const int lane = vw::lane();
 	int pos = 0;
+	nph = 0;
 	unsigned char *curblk = kp.curblk + (size_t) ch * 2048;
 
 	while (pos < nd) {
 		if (R.state == VDL2_ST_WSYNC) {
-			/* ---- idle mode: up to 32 steps at dumps p0, p0+2, ... (d8psk.c:248-313) ---- */
-			if (R.clk >= 8)
-				R.clk &= 7;	/* unreachable for finite input (clk < 8 whenever the burst clock was sane) */
-			const int c4 = R.clk >= 4;
-			const int p0 = pos + (c4 ? 0 : 1);
-			const int r = c4 ? R.clk - 4 : R.clk;
-			if (p0 >= nd) {
-				R.clk += 4 * (nd - pos);
-				pos = nd;
-				break;
-			}
-			const int nsteps = ((nd - 1 - p0) >> 1) + 1;
-			const int nb = nsteps < 32 ? nsteps : 32;
-			float m[17];
-#pragma unroll
-			for (int j = 0; j < 17; j++)
-				m[j] = c_tab.mflt[r + 4 * j];	/* r + 64 <= 67: zero padded */
-			const int d = p0 + 2 * lane;
-			float Pn = 0.f;
-			if (lane < nb)
-				Pn = filt_phase17(sd, d, m);
-			phb[VDL2_PHHIST + lane] = Pn;
-			vw::sync();
-			float err, fr;
-			sync_fit(phb + lane, err, fr);
-			const float e1 = vw::shfl_up(err, 1), e2 = vw::shfl_up(err, 2), f1 = vw::shfl_up(fr, 1);
-			const float perr_l = lane >= 1 ? e1 : R.perr;
-			const float p2err_l = lane >= 2 ? e2 : (lane == 1 ? R.perr : R.p2err);
-			const float pfr_l = lane >= 1 ? f1 : R.pfr;
-			const bool trig = (lane < nb) && (perr_l < 4.0f) && (err > perr_l);
-			const unsigned tm = vw::ballot(trig);
-			const int K = tm ? vw::ffs(tm) : nb;	/* steps committed, trigger step included */
-
-			if ((kp.taps & VDL2_TAP_STEPS_BIT) && lane < K) {
-				const unsigned idx = R.n_steps + lane;
-				if (idx < kp.cap_steps) {
-					Vdl2StepRec s;
-					s.dump = dump_base + d;
-					s.P = Pn;
-					const bool tl = tm && lane == K - 1;
-					s.err = tl ? -1.0f : err;
-					s.fr = tl ? pfr_l : fr;
-					s.pad = 0;
-					kp.tap_steps[(size_t) ch * kp.cap_steps + idx] = s;
-				}
-			}
-			R.n_steps += (kp.taps & VDL2_TAP_STEPS_BIT) ? K : 0;
-
-			/* commit K phases: slide the 64-entry history */
-			const float k0 = phb[lane + K], k1 = phb[lane + 32 + K];
-			vw::sync();
-			phb[lane] = k0;
-			phb[lane + 32] = k1;
-			vw::sync();
-
-			if (!tm) {
-				const float eL = vw::shfl(err, K - 1), fL = vw::shfl(fr, K - 1);
-				const float eP = vw::shfl(err, K >= 2 ? K - 2 : 0);
-				R.p2err = K >= 2 ? eP : R.perr;
-				R.perr = eL;
-				R.pfr = fL;
-				pos = p0 + 2 * (K - 1) + 1;
-				R.clk = r;
-			} else {
-				/* trigger (d8psk.c:292-308) at step T = K-1 */
-				const int T = K - 1;
-				const float eT = vw::shfl(err, T), pT = vw::shfl(perr_l, T);
-				const float p2T = vw::shfl(p2err_l, T), fT = vw::shfl(pfr_l, T);
-				const int dT = p0 + 2 * T;
-				R.state = VDL2_ST_GETHEAD;
-				R.symidx = 0;
-				R.df = fT;
-				R.ppm = (float)((double)vw::fmul(10500.0f, R.df) / (2.0 * VDL2_PI_D * (double)Fr) * 1e6);
-				const float num = vw::fmul(4.0f, vw::fadd(vw::fsub(p2T, vw::fmul(4.0f, pT)), vw::fmul(3.0f, eT)));
-				const float den = vw::fadd(vw::fsub(p2T, vw::fmul(2.0f, pT)), eT);
-				const float of = vw::fdiv(num, den);
-				int nclk = (int)roundf(of);
-				nclk = nclk < 0 ? 0 : (nclk > 64 ? 64 : nclk);	/* of is in [4,12] for finite input */
-				R.clk = nclk;
-				R.P1 = filt_phase_any(sd, dT, nclk);
-				R.perr = R.p2err = 500.f;
-				R.sync_dump = dump_base + dT;
-				if ((kp.taps & VDL2_TAP_SYNCS_BIT)) {
-					if (lane == 0 && R.n_syncs < kp.cap_syncs) {
-						Vdl2SyncRec s;
-						s.dump = R.sync_dump;
-						s.clk = nclk;
-						s.df = R.df;
-						s.ppm = R.ppm;
-						s.P1 = R.P1;
-						kp.tap_syncs[(size_t) ch * kp.cap_syncs + R.n_syncs] = s;
-					}
-					R.n_syncs++;
-				}
-				pos = dT + 1;
-			}
+			idle_run(kp, ch, Fr, R, sd, S, nd, dump_base, pos, nph);
 		} else {
 			/* ---- burst: up to 32 symbols at dumps ds0, ds0+8, ... (d8psk.c:314-332) ---- */
 			const int c = R.clk;

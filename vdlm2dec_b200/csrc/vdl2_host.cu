@@ -382,7 +382,8 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.outq_count = h->d_outq_count;
 	kp.outq_cap = h->outq_cap;
 	kp.dropped = h->d_dropped;
-	kp.taps = h->cfg.taps;
+	kp.taps = h->cfg.taps & 15u;
+	kp.flags = (h->cfg.taps & VDL2_OPT_EXACT_IDLE) ? VDL2_FLAG_NO_SCREEN : 0u;
 	kp.tap_dumps = h->d_tap_dumps;
 	kp.tap_steps = h->d_tap_steps;
 	kp.tap_syncs = h->d_tap_syncs;

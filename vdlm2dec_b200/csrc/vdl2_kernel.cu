@@ -257,9 +257,14 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	unsigned char *stage0 = smem;
 	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + NSTAGE * STAGE_BYTES);
 	float2 *sd = reinterpret_cast < float2 * >(smem + NSTAGE * STAGE_BYTES + 64);
-	float *phb = reinterpret_cast < float *>(sd + VDL2_HIST + VDL2_TILE_DUMPS);
-	float *hv = phb + 96;
+	float *hv = reinterpret_cast < float *>(sd + VDL2_HIST + VDL2_TILE_DUMPS);
 	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
+	/* phase 2 scratch lives in the TMA stages, which are idle while a tile is demodulated */
+	IdleScratch scr;
+	scr.pht = reinterpret_cast < float *>(stage0);
+	scr.vw = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4);
+	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
+	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_CAND_CAP * 2 <= NSTAGE * STAGE_BYTES, "phase 2 scratch must fit the stages");
 
 	if ((smem_u32(smem) & 1023u) != 0)
 		__trap();	/* the 128B swizzle pattern assumes 1 KiB aligned stages */
@@ -342,8 +347,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		Vdl2ChanState *gs = kp.state + ch;
 		if (lane < VDL2_HIST)
 			sd[lane] = make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane));
-		phb[lane] = __ldcg(gs->ph + lane);
-		phb[lane + 32] = __ldcg(gs->ph + lane + 32);
+		scr.pht[lane] = __ldcg(gs->ph + lane);
+		scr.pht[lane + 32] = __ldcg(gs->ph + lane + 32);
 		if (lane < 28)
 			hv[lane] = __ldcg(gs->hv + lane);
 		ChanRegs R;
@@ -379,7 +384,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		}
 
 		/* ---- phase 2 ---- */
-		demod_tile(kp, ch, chn, Fr, R, sd, phb, hv, nd, dump_base);
+		int nph = 0;
+		demod_tile(kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph);
 		__syncwarp();
 
 		/* ---- store state, release the channel ---- */
@@ -388,8 +394,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			gs->hist_re[lane] = h.x;
 			gs->hist_im[lane] = h.y;
 		}
-		gs->ph[lane] = phb[lane];
-		gs->ph[lane + 32] = phb[lane + 32];
+		gs->ph[lane] = scr.pht[nph + lane];
+		gs->ph[lane + 32] = scr.pht[nph + lane + 32];
 		if (lane < 28)
 			gs->hv[lane] = hv[lane];
 		if (lane == 0) {
@@ -426,7 +432,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 /* ------------------------------------------------------------------ launch shims used by vdl2_host.cu */
 extern "C" int vdl2_kernel_smem_bytes(int nco_entries)
 {
-	return VDL2_NSTAGE * STAGE_BYTES + 64 + (VDL2_HIST + VDL2_TILE_DUMPS) * 8 + 96 * 4 + 32 * 4 + nco_entries * 16;
+	return VDL2_NSTAGE * STAGE_BYTES + 64 + (VDL2_HIST + VDL2_TILE_DUMPS) * 8 + 32 * 4 + nco_entries * 16;
 }
 
 template < int FMT > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
