@@ -58,6 +58,15 @@ def _capture(tmp_path, chans, nblk=60, seed=3, acars=False):
     return str(path), nb
 
 
+def _expected_blocks(cap, fos):
+    """How many blocks the REFERENCE algorithm completes on this capture as rtl.c delivers it (index quirk
+    of rtl.c:285-292 included): the single-threaded oracle, one channel at a time.  A false trigger on a
+    glitch can park a channel in a phantom multi-row burst, so this can be fewer than the bursts sent."""
+    from oracle.pyoracle import Oracle
+    iq = np.fromfile(cap, dtype=np.uint8)
+    return sum(len(Oracle("port", Fo=fo).feed(iq, "rtl_quirk").blocks) for fo in fos)
+
+
 def _run(binary, cap, freqs, extra=()):
     env = dict(os.environ, VDL2_FAKE_IQ=cap)
     p = subprocess.run([binary, *extra, "-v", "-r", "0", *freqs], env=env, capture_output=True, text=True, timeout=300)
@@ -94,7 +103,8 @@ def test_dropin_text_identical(tmp_path, freqs):
     ref_out, _ = _run(CPU_BIN, cap, freqs, extra=ALL)
     gpu_out, gpu_err = _run(GPU_BIN, cap, freqs, extra=ALL)
     a, b = _messages(ref_out), _messages(gpu_out)
-    assert len(b) == nb, f"GPU binary printed {len(b)} of {nb} messages\n{gpu_err[-1500:]}"
+    want = _expected_blocks(cap, fos)
+    assert len(b) == want, f"GPU binary printed {len(b)} of {want} messages\n{gpu_err[-1500:]}"
     if len(freqs) == 1:
         assert a == b
     else:
@@ -102,7 +112,7 @@ def test_dropin_text_identical(tmp_path, freqs):
         # (viterbi.c:25-27, called from d8psk.c:83,88,300 without a lock): overlapping headers corrupt
         # each other and the all-CPU binary drops bursts depending on thread timing.  Everything it
         # does print must be printed identically by the GPU build, which decodes headers per channel.
-        assert set(a) <= set(b) and len(a) >= nb // 2, (len(a), len(b), nb)
+        assert set(a) <= set(b) and len(a) >= want // 2, (len(a), len(b), want)
 
 
 @pytest.mark.gpu
@@ -116,5 +126,6 @@ def test_dropin_acars_json_identical(tmp_path):
     b = _run(GPU_BIN, cap, freqs, extra=("-J",))[0]
     ja = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in a.splitlines() if l.startswith("{"))
     jb = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in b.splitlines() if l.startswith("{"))
-    assert len(jb) == nb and set(ja) <= set(jb) and len(ja) >= nb // 2  # see the race note above
+    want = _expected_blocks(cap, [-50_000, -175_000])
+    assert len(jb) == want and set(ja) <= set(jb) and len(ja) >= want // 2  # see the race note above
     assert '"text":"HELLO VDL2 NUMBER 0' in "".join(ja)

@@ -31,6 +31,15 @@ extern int nbch;		/* main.c:59 */
 static channel_t *g_ch[MAXNBCHANNELS];
 static vdl2_chan_param_t g_par[MAXNBCHANNELS];
 static vdl2gpu_t *g_gpu;
+static pthread_mutex_t g_busy = PTHREAD_MUTEX_INITIALIZER;
+
+/* main.c:246 calls exit(1) as soon as the SDR stops, while workers may still be inside the last
+   block.  Registered after the CUDA runtime's own atexit hook (so it runs before it): wait for the
+   block in flight instead of tearing the context down under it. */
+static void quiesce(void)
+{
+	pthread_mutex_lock(&g_busy);
+}
 
 int initD8psk(channel_t * ch)
 {				/* same fields the reference sets (d8psk.c:28-37); the demodulator state itself lives on the GPU */
@@ -76,12 +85,14 @@ static void gpu_open(void)
 	cfg.max_blocks = 1024;
 	if (vdl2_create(&cfg, g_par, &g_gpu))
 		die("vdl2_create");
+	atexit(quiesce);
 }
 
 static void gpu_block(void)
 {
 	static vdl2_block_t out[1024];
 	int n = 0;
+	pthread_mutex_lock(&g_busy);
 	if (vdl2_process_host(g_gpu, Cbuff, RTLINBUFSZ / 2, 0))
 		die("vdl2_process_host");
 	if (vdl2_drain_blocks(g_gpu, out, 1024, &n))
@@ -102,6 +113,7 @@ static void gpu_block(void)
 			memcpy(blk->data[r], out[i].data[r], 255);
 		decodeVdlm2(ch);	/* takes blk, installs a fresh zeroed one (vdlm2.c:189-205) */
 	}
+	pthread_mutex_unlock(&g_busy);
 }
 
 void *rcv_thread(void *arg)
