@@ -146,6 +146,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	std::vector < float >pht(VDL2_PHT_LEN, 0.f);
 	std::vector < float2 > vwin(96);
 	std::vector < unsigned short >cand(VDL2_CAND_CAP);
+	std::vector < float2 > win(VDL2_WIN_LEN);
 	for (int i = 0; i < VDL2_HIST; i++)
 		sd[i] = make_float2(0.f, 0.f);
 	vdl2::ChanRegs R;
@@ -168,6 +169,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 		job.S.pht = pht.data();
 		job.S.vw = vwin.data();
 		job.S.cand = cand.data();
+		job.S.win = win.data();
 		job.hv = hv;
 		job.R0 = R;
 		run_warp(&job);

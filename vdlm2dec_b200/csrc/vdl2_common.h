@@ -50,7 +50,8 @@ struct Vdl2Tables {
 	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
 	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
 	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
-	unsigned char sched[VDL2_MAX_CHUNKS];	/* mixer: last sample of a dump inside each 16-byte chunk, or samples-per-chunk */
+	unsigned sched_box[VDL2_MAX_CHUNKS / 8];	/* mixer: per 128-byte box, 8 nibbles: last sample of a dump inside
+						   each 16-byte chunk, or samples-per-chunk if the dump continues */
 	float scale[VDL2_DUMPS_PER_ROW];	/* mixer: 1/nf of each dump of a row */
 	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
 };
@@ -83,6 +84,7 @@ struct Vdl2KParams {
 	unsigned *ticket;	/* work counter */
 	int *progress;		/* [nch]: tiles completed in this launch */
 	uint8_t *curblk;	/* [nch][2048] block under construction */
+	float2 *scratch;	/* [grid][VDL2_HIST + VDL2_TILE_DUMPS]: decimated stream of the tile a warp works on */
 	Vdl2BlockRec *outq;
 	unsigned *outq_count;
 	unsigned outq_cap;

@@ -94,23 +94,9 @@ VQ float filt_phase_any(const float2 * sd, int d, int clk)
 	int j = 0;
 	for (int i = clk; i < VDL2_MFLTLEN; i += 4, j++) {
 		const float m = c_tab.mflt[i];
-		const float2 x = sd[d + j];
+		const float2 x = vw::ldcg(sd + d + j);
 		sr = vw::fma(x.x, m, sr);
 		si = vw::fma(x.y, m, si);
-	}
-	return vw::atan2(si, sr);
-}
-
-/* same, steady state: r in 0..3 -> 17 taps (tap 64 is the implicit zero when r = 0, and
-   r + 64 > 64 reads the zero padding of the table for r > 0) */
-VQ float filt_phase17(const float2 * sd, int d, const float *m)
-{
-	float sr = 0.f, si = 0.f;
-#pragma unroll
-	for (int j = 0; j < 17; j++) {
-		const float2 x = sd[d + j];
-		sr = vw::fma(x.x, m[j], sr);
-		si = vw::fma(x.y, m[j], si);
 	}
 	return vw::atan2(si, sr);
 }
@@ -254,7 +240,7 @@ VQ unsigned header_decode(const float *hv)
 
 /* ---------------------------------------------------------------------------------------
  * demod_tile: consume dumps [0, nd) of one tile.
- *   sd   : shared, float2[16 + nd], sd[16 + i] = dump i, sd[0..15] = history
+ *   sd   : float2[16 + nd] (L2-resident scratch of this warp), sd[16 + i] = dump i, sd[0..15] = history
  *   S    : shared scratch of the idle search; S.pht[0..63] = the 64 previous idle-mode phases (oldest
  *          first); on return nph phases were appended (the new history is S.pht[nph .. nph+63])
  *   hv   : shared, float[28]; header soft bits collected so far
@@ -302,10 +288,12 @@ VQ void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long
 /* scratch of the idle-mode search (shared memory; the kernel lends it the idle TMA stages) */
 #define VDL2_PHT_LEN (VDL2_PHHIST + VDL2_TILE_DUMPS / 2 + 32)
 #define VDL2_CAND_CAP 192
+#define VDL2_WIN_LEN 80
 struct IdleScratch {
 	float *pht;		/* [VDL2_PHT_LEN]: pht[0..63] = the 64 phases before the tile, then one per idle step */
 	float2 *vw;		/* [96]: differential phasors v_t = z_t conj(z_{t-4}), sliding window */
 	unsigned short *cand;	/* [VDL2_CAND_CAP]: steps that passed the screen */
+	float2 *win;		/* [VDL2_WIN_LEN]: the dumps one batch of 32 steps filters (copied from the L2-resident stream) */
 };
 
 /* filter only (no phase): 17 taps, steady-state tap phase */
@@ -417,9 +405,15 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 	}
 	for (int b0 = 0; b0 < N; b0 += 32) {
 		const int k = b0 + lane;
+		/* the 79 dumps this batch filters: sd[p0 + 2*b0 .. +78] -> shared window */
+		for (int i = lane; i < VDL2_WIN_LEN; i += 32) {
+			const int g = p0 + 2 * b0 + i;
+			S.win[i] = g < VDL2_HIST + nd ? vw::ldcg(sd + g) : make_float2(0.f, 0.f);
+		}
+		vw::sync();
 		float sr = 1.f, si = 0.f;
 		if (k < N)
-			filt17(sd, p0 + 2 * k, m, sr, si);
+			filt17(S.win, 2 * lane, m, sr, si);
 		const float P = vw::atan2(si, sr);
 		if (k < N)
 			ph[VDL2_PHHIST + k] = P;
@@ -461,10 +455,9 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 			vw::sync();
 			S.vw[lane] = w1;
 			S.vw[32 + lane] = w2;
-			vw::sync();
 		}
+		vw::sync();
 	}
-	vw::sync();
 
 	/* ---- pass B: exact fit of the candidates, in time order, until the first err < 4 ---- */
 	int s0 = exact_only || overflow ? 0 : -1;	/* first step of the exact search; -1: no trigger possible in this run */

@@ -47,6 +47,7 @@ struct vdl2gpu {
 	unsigned *d_ticket;
 	int *d_progress;
 	uint8_t *d_curblk;
+	float2 *d_scratch;
 	Vdl2BlockRec *d_outq;
 	unsigned *d_outq_count, *d_dropped;
 	unsigned outq_cap;
@@ -127,14 +128,18 @@ static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
 	memcpy(t.hcol, hc, sizeof hc);
 	/* dump schedule of one row (d8psk.c:374-381) */
 	int clk = 0, nf = 0, k = 0;
-	for (int c = 0; c < h->chunks_per_row; c++)
-		t.sched[c] = (unsigned char)h->spc;
+	for (int c = 0; c < VDL2_MAX_CHUNKS; c++)
+		t.sched_box[c >> 3] |= (unsigned)h->spc << (4 * (c & 7));
 	for (int n = 0; n < h->row_samples; n++) {
 		nf++;
 		clk += 21;
 		if (clk >= (int)h->cfg.sdrclk) {
 			clk %= (int)h->cfg.sdrclk;
-			t.sched[n / h->spc] = (unsigned char)(n % h->spc);
+			{
+				const int c = n / h->spc;
+				t.sched_box[c >> 3] &= ~(15u << (4 * (c & 7)));
+				t.sched_box[c >> 3] |= (unsigned)(n % h->spc) << (4 * (c & 7));
+			}
 			if (k < VDL2_DUMPS_PER_ROW)
 				t.scale[k] = 1.0f / (float)nf;
 			k++;
@@ -277,6 +282,8 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	CK(h, cudaMalloc(&h->d_progress, sizeof(int) * nch));
 	CK(h, cudaMalloc(&h->d_curblk, (size_t) nch * 2048));
 	CK(h, cudaMemset(h->d_curblk, 0, (size_t) nch * 2048));
+	CK(h, cudaMalloc(&h->d_scratch, sizeof(float2) * (size_t) h->grid * (VDL2_HIST + VDL2_TILE_DUMPS)));
+	CK(h, cudaMemset(h->d_scratch, 0, sizeof(float2) * (size_t) h->grid * (VDL2_HIST + VDL2_TILE_DUMPS)));
 	h->outq_cap = cfg->max_blocks > 0 ? (unsigned)cfg->max_blocks : (unsigned)std::max(4096, nch * 8);
 	CK(h, cudaMalloc(&h->d_outq, sizeof(Vdl2BlockRec) * (size_t) h->outq_cap));
 
@@ -328,6 +335,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_curblk);
+	cudaFree(h->d_scratch);
 	cudaFree(h->d_outq);
 	cudaFree(h->d_tap_dumps);
 	cudaFree(h->d_tap_steps);
@@ -378,6 +386,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.ticket = h->d_ticket;
 	kp.progress = h->d_progress;
 	kp.curblk = h->d_curblk;
+	kp.scratch = h->d_scratch;
 	kp.outq = h->d_outq;
 	kp.outq_count = h->d_outq_count;
 	kp.outq_cap = h->outq_cap;

@@ -14,7 +14,8 @@
  *     land 128B-swizzled in a 3-stage mbarrier ring, which transposes time-major HBM into
  *     lane-major shared memory: lane r reads 16-byte chunk j of its row at (j ^ (r&7))<<4,
  *     conflict free.  Bytes are widened with PRMT magic-number tricks (exact), the complex
- *     MAC runs as packed FFMA2 on sample pairs, dumps go to shared memory in time order.
+ *     MAC runs as packed FFMA2 on sample pairs; dumps go, in time order, to a per-warp scratch that
+ *     stays L2 resident (21.6 KB per warp), which keeps shared memory per warp at 13 KB -> 16 warps/SM.
  *   phase 2 (demodulator): vdl2_demod.cuh, lanes over consecutive steps / symbols.
  *
  * Phase 1 needs no channel state, so a warp mixes tile t of a channel while another warp
@@ -107,7 +108,7 @@ __device__ __forceinline__ void dump_close(MixAcc & a, float2 * sdrow, int &k)
 	const float s = c_tab.scale[k];
 	const float re = (a.A.x + a.A.y) - (a.B.x + a.B.y);
 	const float im = (a.C.x + a.C.y) + (a.G.x + a.G.y);
-	sdrow[k] = fmul2(make_float2(re, im), make_float2(s, s));
+	__stcg(sdrow + k, fmul2(make_float2(re, im), make_float2(s, s)));
 	k++;
 	acc_zero(a);
 }
@@ -249,22 +250,25 @@ template < int FMT > __device__ __forceinline__ void chunk_any(int kind, MixAcc 
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template < int FMT > __global__ void __launch_bounds__(32, 1)
+template < int FMT > __global__ void __launch_bounds__(32, 16)
 vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const int lane = threadIdx.x;
 	unsigned char *stage0 = smem;
 	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + NSTAGE * STAGE_BYTES);
-	float2 *sd = reinterpret_cast < float2 * >(smem + NSTAGE * STAGE_BYTES + 64);
-	float *hv = reinterpret_cast < float *>(sd + VDL2_HIST + VDL2_TILE_DUMPS);
+	float *hv = reinterpret_cast < float *>(smem + NSTAGE * STAGE_BYTES + 64);
 	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
+	/* the decimated stream of the tile lives in global memory (L2): sd[0..15] history, sd[16 + i] dump i */
+	float2 *sd = kp.scratch + (size_t) blockIdx.x * (VDL2_HIST + VDL2_TILE_DUMPS);
 	/* phase 2 scratch lives in the TMA stages, which are idle while a tile is demodulated */
 	IdleScratch scr;
 	scr.pht = reinterpret_cast < float *>(stage0);
 	scr.vw = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4);
-	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
-	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_CAND_CAP * 2 <= NSTAGE * STAGE_BYTES, "phase 2 scratch must fit the stages");
+	scr.win = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
+	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8);
+	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + VDL2_CAND_CAP * 2 <= NSTAGE * STAGE_BYTES,
+		      "phase 2 scratch must fit the stages");
 
 	if ((smem_u32(smem) & 1023u) != 0)
 		__trap();	/* the 128B swizzle pattern assumes 1 KiB aligned stages */
@@ -278,7 +282,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	uint32_t phases = 0;	/* parity bit per stage */
 	const int nitems = kp.ntiles * kp.nch;
 	const int wpc = FmtTraits < FMT >::wper_chunk;
-	const int last_chunks = kp.chunks_per_row - 8 * (kp.nbox - 1);
+	const int nbox = kp.nbox, nco = kp.nco_pairs;
+	const int last_chunks = kp.chunks_per_row - 8 * (nbox - 1);
 	const uint32_t l7 = (uint32_t) (lane & 7);
 	float2 *sdrow = sd + VDL2_HIST + VDL2_DUMPS_PER_ROW * lane;
 
@@ -298,42 +303,48 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 
 		/* prologue: first boxes in flight, oscillator table to shared memory */
 		if (lane == 0) {
-			for (int b = 0; b < NSTAGE && b < kp.nbox; b++) {
+			for (int b = 0; b < NSTAGE && b < nbox; b++) {
 				const uint32_t bar = smem_u32(bars + b);
 				mbar_expect_tx(bar, STAGE_BYTES);
 				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream);
 			}
 		}
-		for (int i = lane; i < kp.nco_pairs; i += 32)
-			wsm[i] = kp.wtab[(size_t) ch * kp.nco_pairs + i];
+		for (int i = lane; i < nco; i += 32)
+			wsm[i] = kp.wtab[(size_t) ch * nco + i];
 		__syncwarp();
 
 		/* ---- phase 1 ---- */
 		MixAcc acc;
 		acc_zero(acc);
-		int k = 0, cidx = 0, widx = 0;
-		for (int b = 0; b < kp.nbox; b++) {
+		int k = 0, widx = 0;
+		for (int b = 0; b < nbox; b++) {
 			const int slot = b % NSTAGE;
 			mbar_wait(smem_u32(bars + slot), (phases >> slot) & 1u);
 			phases ^= 1u << slot;
 			const unsigned char *rowp = stage0 + slot * STAGE_BYTES + lane * 128;
-			const int nchunk = (b == kp.nbox - 1) ? last_chunks : 8;
+			const int nchunk = (b == nbox - 1) ? last_chunks : 8;
+			unsigned kinds = c_tab.sched_box[b];	/* one nibble per chunk */
+			/* software pipeline: chunk j+1 is in flight while chunk j is converted and mixed */
+			uint4 vnext = *reinterpret_cast < const uint4 * >(rowp + (l7 << 4));
 #pragma unroll 1
 			for (int j = 0; j < nchunk; j++) {
-				const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
-				const int kind = c_tab.sched[cidx++];
+				const uint4 v = vnext;
+				const int jn = j + 1 < nchunk ? j + 1 : j;
+				vnext = *reinterpret_cast < const uint4 * >(rowp + ((jn ^ l7) << 4));
+				const int kind = kinds & 15u;
+				kinds >>= 4;
 				chunk_any < FMT > (kind, acc, v, wsm + widx, sdrow, k);
 				widx += wpc;
-				if (widx >= kp.nco_pairs)
-					widx = 0;
+				widx = widx >= nco ? 0 : widx;
 			}
 			__syncwarp();
-			if (lane == 0 && b + NSTAGE < kp.nbox) {
+			if (lane == 0 && b + NSTAGE < nbox) {
 				const uint32_t bar = smem_u32(bars + slot);
 				mbar_expect_tx(bar, STAGE_BYTES);
 				tma_load_3d(smem_u32(stage0 + slot * STAGE_BYTES), &tmap, bar, (b + NSTAGE) * 32, row0, stream);
 			}
 		}
+		__threadfence_block();
 		__syncwarp();
 
 		/* ---- wait for the previous tile of this channel, load its state ---- */
@@ -346,7 +357,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		__threadfence();
 		Vdl2ChanState *gs = kp.state + ch;
 		if (lane < VDL2_HIST)
-			sd[lane] = make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane));
+			__stcg(sd + lane, make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane)));
 		scr.pht[lane] = __ldcg(gs->ph + lane);
 		scr.pht[lane + 32] = __ldcg(gs->ph + lane + 32);
 		if (lane < 28)
@@ -370,6 +381,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		R.n_steps = __ldcg(&gs->n_steps);
 		R.n_syncs = __ldcg(&gs->n_syncs);
 		R.n_syms = __ldcg(&gs->n_syms);
+		__threadfence_block();
 		unsigned n_dumps = __ldcg(&gs->n_dumps);
 		const int chn = __ldcg(&gs->chn), Fr = __ldcg(&gs->Fr);
 		__syncwarp();
@@ -379,7 +391,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			float2 *dst = kp.tap_dumps + (size_t) ch * kp.cap_dumps;
 			for (int i = lane; i < nd; i += 32)
 				if (n_dumps + i < kp.cap_dumps)
-					dst[n_dumps + i] = sd[VDL2_HIST + i];
+					dst[n_dumps + i] = __ldcg(sd + VDL2_HIST + i);
 			n_dumps += nd;
 		}
 
@@ -390,7 +402,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 
 		/* ---- store state, release the channel ---- */
 		if (lane < VDL2_HIST) {
-			const float2 h = sd[nd + lane];	/* last 16 dumps of the tile */
+			const float2 h = __ldcg(sd + nd + lane);	/* last 16 dumps of the tile */
 			gs->hist_re[lane] = h.x;
 			gs->hist_im[lane] = h.y;
 		}
@@ -432,7 +444,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 /* ------------------------------------------------------------------ launch shims used by vdl2_host.cu */
 extern "C" int vdl2_kernel_smem_bytes(int nco_entries)
 {
-	return VDL2_NSTAGE * STAGE_BYTES + 64 + (VDL2_HIST + VDL2_TILE_DUMPS) * 8 + 32 * 4 + nco_entries * 16;
+	return VDL2_NSTAGE * STAGE_BYTES + 64 + 32 * 4 + nco_entries * 16;
 }
 
 template < int FMT > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
