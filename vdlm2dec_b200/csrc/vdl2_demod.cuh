@@ -309,6 +309,17 @@ VQ void filt17(const float2 * sd, int d, const float *m, float &sr, float &si)
 	}
 }
 
+/* three independent L2 loads per lane: window entries lane, lane+32, lane+64 starting at sd[g0] */
+VQ void win_fetch(const float2 * sd, int g0, int glim, float2 & wa, float2 & wb, float2 & wc)
+{
+	const int l = vw::lane();
+	const float2 z = make_float2(0.f, 0.f);
+	const int ga = g0 + l, gb = g0 + l + 32, gc = g0 + l + 64;
+	wa = ga < glim ? vw::ldcg(sd + ga) : z;
+	wb = gb < glim ? vw::ldcg(sd + gb) : z;
+	wc = (l < VDL2_WIN_LEN - 64 && gc < glim) ? vw::ldcg(sd + gc) : z;
+}
+
 VQ float2 cmul_conj(float2 a, float2 b)
 {				/* a * conj(b) */
 	return make_float2(vw::fma(a.x, b.x, a.y * b.y), vw::fma(a.y, b.x, -(a.x * b.y)));
@@ -403,14 +414,18 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		zlast = zB;
 		vw::sync();
 	}
+	float2 wa, wb, wc;
+	win_fetch(sd, p0, VDL2_HIST + nd, wa, wb, wc);
 	for (int b0 = 0; b0 < N; b0 += 32) {
 		const int k = b0 + lane;
-		/* the 79 dumps this batch filters: sd[p0 + 2*b0 .. +78] -> shared window */
-		for (int i = lane; i < VDL2_WIN_LEN; i += 32) {
-			const int g = p0 + 2 * b0 + i;
-			S.win[i] = g < VDL2_HIST + nd ? vw::ldcg(sd + g) : make_float2(0.f, 0.f);
-		}
+		/* the 79 dumps this batch filters, sd[p0 + 2*b0 .. +78], were fetched from L2 one batch ahead */
+		S.win[lane] = wa;
+		S.win[lane + 32] = wb;
+		if (lane < VDL2_WIN_LEN - 64)
+			S.win[lane + 64] = wc;
 		vw::sync();
+		if (b0 + 32 < N)
+			win_fetch(sd, p0 + 2 * (b0 + 32), VDL2_HIST + nd, wa, wb, wc);
 		float sr = 1.f, si = 0.f;
 		if (k < N)
 			filt17(S.win, 2 * lane, m, sr, si);

@@ -57,10 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 		      "@p bra DONE_%=;\n" "bra WAIT_%=;\n" "DONE_%=:\n" "}"::"r" (bar), "r"(parity):"memory");
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2,
+					    unsigned long long policy)
 {
-	asm volatile ("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-		      " [%0], [%1, {%3, %4, %5}], [%2];"::"r" (dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+	asm volatile ("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+		      " [%0], [%1, {%3, %4, %5}], [%2], %6;"::"r" (dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
 		      :"memory");
 }
 
@@ -282,7 +283,11 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	uint32_t phases = 0;	/* parity bit per stage */
 	const int nitems = kp.ntiles * kp.nch;
 	const int wpc = FmtTraits < FMT >::wper_chunk;
-	const int nbox = kp.nbox, nco = kp.nco_pairs;
+	const int nbox = kp.nbox;
+	int nco = kp.nco_pairs;
+	asm volatile ("":"+r" (nco));	/* keep the wrap limit in a register (ptxas otherwise reloads the parameter per chunk) */
+	unsigned long long l2pol;	/* the input is read exactly once: evict-first keeps the per-warp scratch L2 resident */
+	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
 	const int last_chunks = kp.chunks_per_row - 8 * (nbox - 1);
 	const uint32_t l7 = (uint32_t) (lane & 7);
 	float2 *sdrow = sd + VDL2_HIST + VDL2_DUMPS_PER_ROW * lane;
@@ -306,7 +311,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			for (int b = 0; b < NSTAGE && b < nbox; b++) {
 				const uint32_t bar = smem_u32(bars + b);
 				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream);
+				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream, l2pol);
 			}
 		}
 		for (int i = lane; i < nco; i += 32)
@@ -341,7 +346,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			if (lane == 0 && b + NSTAGE < nbox) {
 				const uint32_t bar = smem_u32(bars + slot);
 				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_3d(smem_u32(stage0 + slot * STAGE_BYTES), &tmap, bar, (b + NSTAGE) * 32, row0, stream);
+				tma_load_3d(smem_u32(stage0 + slot * STAGE_BYTES), &tmap, bar, (b + NSTAGE) * 32, row0, stream, l2pol);
 			}
 		}
 		__threadfence_block();
