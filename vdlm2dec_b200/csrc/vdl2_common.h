@@ -50,9 +50,8 @@ struct Vdl2Tables {
 	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
 	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
 	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
-	unsigned sched_box[VDL2_MAX_CHUNKS / 8];	/* mixer: per 128-byte box, 8 nibbles: last sample of a dump inside
-						   each 16-byte chunk, or samples-per-chunk if the dump continues */
-	float scale[VDL2_DUMPS_PER_ROW];	/* mixer: 1/nf of each dump of a row */
+	unsigned short sched_dump[VDL2_DUMPS_PER_ROW];	/* mixer: per dump of a row, (E << 8) | np: np whole 16-byte chunks, then
+							   the chunk in which the dump ends after sample E */
 	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
 };
 
@@ -81,6 +80,7 @@ struct Vdl2KParams {
 	int64_t dump_base;	/* global dump index of row 0 of this launch */
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
+	const float4 *dcorr;	/* [nch][84]: per dump (1/nf, 1/nf, -cre/nf, -cim/nf), see dump_close */
 	unsigned *ticket;	/* work counter */
 	int *progress;		/* [nch]: tiles completed in this launch */
 	uint8_t *curblk;	/* [nch][2048] block under construction */

@@ -44,6 +44,7 @@ struct vdl2gpu {
 	/* device */
 	Vdl2ChanState *d_state;
 	float4 *d_wtab;
+	float4 *d_dcorr;
 	unsigned *d_ticket;
 	int *d_progress;
 	uint8_t *d_curblk;
@@ -126,24 +127,18 @@ static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
 		0x19, 0x1a, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f, 0x10, 0x08, 0x04, 0x02, 0x01
 	};			/* viterbi.c:29-35 */
 	memcpy(t.hcol, hc, sizeof hc);
-	/* dump schedule of one row (d8psk.c:374-381) */
-	int clk = 0, nf = 0, k = 0;
-	for (int c = 0; c < VDL2_MAX_CHUNKS; c++)
-		t.sched_box[c >> 3] |= (unsigned)h->spc << (4 * (c & 7));
+	/* dump schedule of one row (d8psk.c:374-381): dump k ends after sample e_k; it consists of np whole
+	   chunks plus the chunk holding e_k (np counts from the chunk after the previous boundary chunk) */
+	int clk = 0, k = 0, prev_c = -1;
 	for (int n = 0; n < h->row_samples; n++) {
-		nf++;
 		clk += 21;
 		if (clk >= (int)h->cfg.sdrclk) {
 			clk %= (int)h->cfg.sdrclk;
-			{
-				const int c = n / h->spc;
-				t.sched_box[c >> 3] &= ~(15u << (4 * (c & 7)));
-				t.sched_box[c >> 3] |= (unsigned)(n % h->spc) << (4 * (c & 7));
-			}
+			const int c = n / h->spc, E = n % h->spc;
 			if (k < VDL2_DUMPS_PER_ROW)
-				t.scale[k] = 1.0f / (float)nf;
+				t.sched_dump[k] = (unsigned short)((E << 8) | (c - prev_c - 1));
+			prev_c = c;
 			k++;
-			nf = 0;
 		}
 	}
 }
@@ -275,6 +270,40 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	CK(h, cudaMalloc(&h->d_wtab, sizeof(float4) * wt.size()));
 	CK(h, cudaMemcpy(h->d_wtab, wt.data(), sizeof(float4) * wt.size(), cudaMemcpyHostToDevice));
 
+	/* per channel, per dump of a row: 1/nf and the cu8 offset correction.  The kernel mixes the exact
+	   integers u-127; the reference mixes u-127.37f (rtl.c:287-289), i.e. (u-127) - delta with
+	   delta = 127.37f - 127 (exact in fp32).  sum (x-delta) w = sum x w - delta sum w, so per dump
+	   re -= delta (sum wr - sum wi), im -= delta (sum wr + sum wi), evaluated here in double. */
+	{
+		std::vector < float4 > dc((size_t) nch * VDL2_DUMPS_PER_ROW);
+		const double delta = (cfg->format == VDL2_FMT_CU8) ? (double)((float)127.37 - 127.0f) : 0.0;
+		for (int c = 0; c < nch; c++) {
+			const float Fo = (float)((float)chans[c].Fo / (float)(cfg->fs) * 2.0 * M_PI);
+			int clk = 0, nf = 0, k = 0;
+			double swr = 0, swi = 0;
+			for (int n = 0; n < h->row_samples; n++) {
+				const float a = (float)(-(n % nco_n)) * Fo;
+				swr += (double)cosf(a);
+				swi += (double)sinf(a);
+				nf++;
+				clk += 21;
+				if (clk >= (int)cfg->sdrclk) {
+					clk %= (int)cfg->sdrclk;
+					const double s = 1.0 / (double)nf;
+					const float sf = 1.0f / (float)nf;
+					if (k < VDL2_DUMPS_PER_ROW)
+						dc[(size_t) c * VDL2_DUMPS_PER_ROW + k] =
+						    make_float4(sf, sf, (float)(-delta * (swr - swi) * s), (float)(-delta * (swr + swi) * s));
+					k++;
+					nf = 0;
+					swr = swi = 0;
+				}
+			}
+		}
+		CK(h, cudaMalloc(&h->d_dcorr, sizeof(float4) * dc.size()));
+		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
+	}
+
 	CK(h, cudaMalloc(&h->d_ticket, 64));
 	CK(h, cudaMemset(h->d_ticket, 0, 64));
 	h->d_outq_count = h->d_ticket + 4;
@@ -332,6 +361,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
+	cudaFree(h->d_dcorr);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_curblk);
@@ -383,6 +413,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.dump_base = h->rows_done * VDL2_DUMPS_PER_ROW;
 	kp.state = h->d_state;
 	kp.wtab = h->d_wtab;
+	kp.dcorr = h->d_dcorr;
 	kp.ticket = h->d_ticket;
 	kp.progress = h->d_progress;
 	kp.curblk = h->d_curblk;

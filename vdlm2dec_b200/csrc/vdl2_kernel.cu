@@ -94,8 +94,8 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 }
 
 /* ------------------------------------------------------------------ phase 1: channeliser */
-struct MixAcc {			/* partial sums of one dump; .x/.y = even/odd sample of a pair */
-	float2 A, B, C, G;	/* A: xr*wr  B: xi*wi  C: xr*wi  G: xi*wr */
+struct MixAcc {			/* partial sums of one dump; .x/.y = even/odd sample of a pair (8-bit formats) */
+	float2 A, B, C, G;	/* A: xr*wr  B: xi*wi  C: xr*wi  G: xi*wr   (cf32: A = (I,Q)*re, C = (I,Q)*im) */
 };
 
 __device__ __forceinline__ void acc_zero(MixAcc & a)
@@ -103,20 +103,29 @@ __device__ __forceinline__ void acc_zero(MixAcc & a)
 	a.A = a.B = a.C = a.G = make_float2(0.f, 0.f);
 }
 
-/* close a dump: D = sum / nf (d8psk.c:377), store in time order */
-__device__ __forceinline__ void dump_close(MixAcc & a, float2 * sdrow, int &k)
+/* close a dump: D = sum / nf (d8psk.c:377) written to the warp's scratch in time order.
+   dc = (1/nf, 1/nf, -cre/nf, -cim/nf): the cu8 path mixes the integers u-127 and removes the
+   remaining 0.37f offset of rtl.c:287-289 here, as delta * sum(w) over the dump's oscillator
+   values (per channel, per dump, exact to one rounding; zero for the other formats). */
+template < int FMT > __device__ __forceinline__ void dump_close(MixAcc & a, float2 * sdrow, const float4 * dcorr, int &k)
 {
-	const float s = c_tab.scale[k];
-	const float re = (a.A.x + a.A.y) - (a.B.x + a.B.y);
-	const float im = (a.C.x + a.C.y) + (a.G.x + a.G.y);
-	__stcg(sdrow + k, fmul2(make_float2(re, im), make_float2(s, s)));
+	const float4 dc = __ldg(dcorr + k);
+	float re, im;
+	if (FMT == VDL2_FMT_CF32) {
+		re = a.A.x - a.C.y;
+		im = a.C.x + a.A.y;
+	} else {
+		re = (a.A.x + a.A.y) - (a.B.x + a.B.y);
+		im = (a.C.x + a.C.y) + (a.G.x + a.G.y);
+	}
+	__stcg(sdrow + k, ffma2(make_float2(re, im), make_float2(dc.x, dc.y), make_float2(dc.z, dc.w)));
 	k++;
 	acc_zero(a);
 }
 
-/* 4 bytes (I0 Q0 I1 Q1) -> exact floats.  PRMT builds 0x4B0000uu = 2^23 + u, one packed
-   add removes the bias; cu8 then subtracts 127.37f exactly like rtl.c:287-289 (u - 127.37f
-   is exact in fp32 for all 256 inputs), cs8 is biased by 128 through the sign-bit flip. */
+/* 4 bytes (I0 Q0 I1 Q1) -> exact floats.  PRMT builds 0x4B0000uu = 2^23 + u and ONE packed add
+   removes the bias: cu8 -> u - 127 (the 0.37f remainder is applied per dump, see dump_close),
+   cs8 -> s (bytes biased by 128 through the sign-bit flip). */
 template < int FMT > __device__ __forceinline__ void cvt_pair8(uint32_t w, float2 & xr, float2 & xi)
 {
 	if (FMT == VDL2_FMT_CS8)
@@ -126,29 +135,23 @@ template < int FMT > __device__ __forceinline__ void cvt_pair8(uint32_t w, float
 	xi.x = __uint_as_float(__byte_perm(w, magic, 0x7441));
 	xr.y = __uint_as_float(__byte_perm(w, magic, 0x7442));
 	xi.y = __uint_as_float(__byte_perm(w, magic, 0x7443));
-	if (FMT == VDL2_FMT_CS8) {
-		const float2 m = make_float2(-8388736.f, -8388736.f);	/* -(2^23 + 128) */
-		xr = fadd2(xr, m);
-		xi = fadd2(xi, m);
-	} else {
-		const float2 m = make_float2(-8388608.f, -8388608.f);
-		const float2 o = make_float2(-127.37f, -127.37f);
-		xr = fadd2(fadd2(xr, m), o);
-		xi = fadd2(fadd2(xi, m), o);
-	}
+	const float bias = (FMT == VDL2_FMT_CS8) ? -8388736.f : -8388735.f;	/* -(2^23 + 128) / -(2^23 + 127) */
+	const float2 m = make_float2(bias, bias);
+	xr = fadd2(xr, m);
+	xi = fadd2(xi, m);
 }
 
 /* one sample pair with its oscillator pair W = (re[n], re[n+1], im[n], im[n+1]).
    SPLIT = 0: both samples in the current dump; 1: dump boundary between them; 2: after them */
-template < int SPLIT > __device__ __forceinline__ void mac_pair(MixAcc & a, float2 xr, float2 xi, float4 W, float2 * sdrow,
-								 int &k)
+template < int FMT, int SPLIT > __device__ __forceinline__ void mac_pair(MixAcc & a, float2 xr, float2 xi, float4 W, float2 * sdrow,
+									const float4 * dcorr, int &k)
 {
 	if (SPLIT == 1) {
 		a.A.x = fmaf(xr.x, W.x, a.A.x);
 		a.B.x = fmaf(xi.x, W.z, a.B.x);
 		a.C.x = fmaf(xr.x, W.z, a.C.x);
 		a.G.x = fmaf(xi.x, W.x, a.G.x);
-		dump_close(a, sdrow, k);
+		dump_close < FMT > (a, sdrow, dcorr, k);
 		a.A.y = xr.y * W.y;
 		a.B.y = xi.y * W.w;
 		a.C.y = xr.y * W.w;
@@ -160,13 +163,14 @@ template < int SPLIT > __device__ __forceinline__ void mac_pair(MixAcc & a, floa
 		a.C = ffma2(xr, wi, a.C);
 		a.G = ffma2(xi, wr, a.G);
 		if (SPLIT == 2)
-			dump_close(a, sdrow, k);
+			dump_close < FMT > (a, sdrow, dcorr, k);
 	}
 }
 
 /* a 16-byte chunk of 8-bit IQ = 8 samples = 4 pairs; E = last sample of the current dump
-   inside this chunk (0..7), or 8 if the dump continues */
-template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+   inside this chunk (0..7), or 8 if the dump continues through the whole chunk */
+template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								    const float4 * dcorr, int &k)
 {
 	const uint32_t d[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
@@ -175,78 +179,68 @@ template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, u
 		cvt_pair8 < FMT > (d[p], xr, xi);
 		const float4 W = w[p];
 		if (E == 2 * p)
-			mac_pair < 1 > (a, xr, xi, W, sdrow, k);
+			mac_pair < FMT, 1 > (a, xr, xi, W, sdrow, dcorr, k);
 		else if (E == 2 * p + 1)
-			mac_pair < 2 > (a, xr, xi, W, sdrow, k);
+			mac_pair < FMT, 2 > (a, xr, xi, W, sdrow, dcorr, k);
 		else
-			mac_pair < 0 > (a, xr, xi, W, sdrow, k);
+			mac_pair < FMT, 0 > (a, xr, xi, W, sdrow, dcorr, k);
 	}
 }
 
-template < int FMT > __device__ __forceinline__ void chunk8_dispatch(int kind, MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
-								      int &k)
-{
-	if (kind == 8) {
-		chunk8 < FMT, 8 > (a, v, w, sdrow, k);
-		return;
-	}
-	switch (kind) {
-	case 0: chunk8 < FMT, 0 > (a, v, w, sdrow, k); break;
-	case 1: chunk8 < FMT, 1 > (a, v, w, sdrow, k); break;
-	case 2: chunk8 < FMT, 2 > (a, v, w, sdrow, k); break;
-	case 3: chunk8 < FMT, 3 > (a, v, w, sdrow, k); break;
-	case 4: chunk8 < FMT, 4 > (a, v, w, sdrow, k); break;
-	case 5: chunk8 < FMT, 5 > (a, v, w, sdrow, k); break;
-	case 6: chunk8 < FMT, 6 > (a, v, w, sdrow, k); break;
-	default: chunk8 < FMT, 7 > (a, v, w, sdrow, k); break;
-	}
-}
-
-/* complex float input (the reference's Cbuff, vdlm2.h:89): a chunk is 2 samples; the
-   oscillator table is stored duplicated, W = (re, re, im, im) per sample, so that the
-   natural (I, Q) register pair feeds FFMA2 directly:
-   A += (I,Q)*(re,re), C += (I,Q)*(im,im);  D = (A.x - C.y) + i (C.x + A.y) */
-template < int E > __device__ __forceinline__ void chunk_cf32(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+/* complex float input (the reference's Cbuff, vdlm2.h:89): a chunk is 2 samples; the oscillator
+   table is stored duplicated, W = (re, re, im, im) per sample, so that the natural (I, Q) register
+   pair feeds FFMA2 directly: A += (I,Q)*(re,re), C += (I,Q)*(im,im); D = (A.x - C.y) + i (C.x + A.y) */
+template < int E > __device__ __forceinline__ void chunk_cf32(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+							       const float4 * dcorr, int &k)
 {
 	const float2 x0 = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
 	const float2 x1 = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
 	const float4 W0 = w[0], W1 = w[1];
 	a.A = ffma2(x0, make_float2(W0.x, W0.y), a.A);
 	a.C = ffma2(x0, make_float2(W0.z, W0.w), a.C);
-	if (E == 0) {
-		a.B = make_float2(a.C.y, 0.f);	/* fold into the common close: re = A.x+A.y - (B.x+B.y) */
-		a.G = make_float2(a.A.y, 0.f);
-		a.A.y = 0.f;
-		a.C.y = 0.f;
-		dump_close(a, sdrow, k);
-	}
+	if (E == 0)
+		dump_close < VDL2_FMT_CF32 > (a, sdrow, dcorr, k);
 	a.A = ffma2(x1, make_float2(W1.x, W1.y), a.A);
 	a.C = ffma2(x1, make_float2(W1.z, W1.w), a.C);
-	if (E == 1) {
-		a.B = make_float2(a.C.y, 0.f);
-		a.G = make_float2(a.A.y, 0.f);
-		a.A.y = 0.f;
-		a.C.y = 0.f;
-		dump_close(a, sdrow, k);
-	}
+	if (E == 1)
+		dump_close < VDL2_FMT_CF32 > (a, sdrow, dcorr, k);
 }
 
 template < int FMT > struct FmtTraits;
-template <> struct FmtTraits <VDL2_FMT_CU8 > { static constexpr int wper_chunk = 4; };
-template <> struct FmtTraits <VDL2_FMT_CS8 > { static constexpr int wper_chunk = 4; };
-template <> struct FmtTraits <VDL2_FMT_CF32 > { static constexpr int wper_chunk = 2; };
+template <> struct FmtTraits <VDL2_FMT_CU8 > { static constexpr int wper_chunk = 4, spc = 8; };
+template <> struct FmtTraits <VDL2_FMT_CS8 > { static constexpr int wper_chunk = 4, spc = 8; };
+template <> struct FmtTraits <VDL2_FMT_CF32 > { static constexpr int wper_chunk = 2, spc = 2; };
 
-template < int FMT > __device__ __forceinline__ void chunk_any(int kind, MixAcc & a, uint4 v, const float4 * w, float2 * sdrow, int &k)
+/* a chunk the current dump runs straight through */
+template < int FMT > __device__ __forceinline__ void chunk_plain(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								  const float4 * dcorr, int &k)
+{
+	if (FMT == VDL2_FMT_CF32)
+		chunk_cf32 < 2 > (a, v, w, sdrow, dcorr, k);
+	else
+		chunk8 < FMT, 8 > (a, v, w, sdrow, dcorr, k);
+}
+
+/* the chunk in which the current dump ends after sample E */
+template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								  const float4 * dcorr, int &k)
 {
 	if (FMT == VDL2_FMT_CF32) {
-		if (kind == 0)
-			chunk_cf32 < 0 > (a, v, w, sdrow, k);
-		else if (kind == 1)
-			chunk_cf32 < 1 > (a, v, w, sdrow, k);
+		if (E == 0)
+			chunk_cf32 < 0 > (a, v, w, sdrow, dcorr, k);
 		else
-			chunk_cf32 < 2 > (a, v, w, sdrow, k);
+			chunk_cf32 < 1 > (a, v, w, sdrow, dcorr, k);
 	} else {
-		chunk8_dispatch < FMT > (kind, a, v, w, sdrow, k);
+		switch (E) {
+		case 0: chunk8 < FMT, 0 > (a, v, w, sdrow, dcorr, k); break;
+		case 1: chunk8 < FMT, 1 > (a, v, w, sdrow, dcorr, k); break;
+		case 2: chunk8 < FMT, 2 > (a, v, w, sdrow, dcorr, k); break;
+		case 3: chunk8 < FMT, 3 > (a, v, w, sdrow, dcorr, k); break;
+		case 4: chunk8 < FMT, 4 > (a, v, w, sdrow, dcorr, k); break;
+		case 5: chunk8 < FMT, 5 > (a, v, w, sdrow, dcorr, k); break;
+		case 6: chunk8 < FMT, 6 > (a, v, w, sdrow, dcorr, k); break;
+		default: chunk8 < FMT, 7 > (a, v, w, sdrow, dcorr, k); break;
+		}
 	}
 }
 
@@ -288,7 +282,6 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	asm volatile ("":"+r" (nco));	/* keep the wrap limit in a register (ptxas otherwise reloads the parameter per chunk) */
 	unsigned long long l2pol;	/* the input is read exactly once: evict-first keeps the per-warp scratch L2 resident */
 	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
-	const int last_chunks = kp.chunks_per_row - 8 * (nbox - 1);
 	const uint32_t l7 = (uint32_t) (lane & 7);
 	float2 *sdrow = sd + VDL2_HIST + VDL2_DUMPS_PER_ROW * lane;
 
@@ -318,37 +311,52 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			wsm[i] = kp.wtab[(size_t) ch * nco + i];
 		__syncwarp();
 
-		/* ---- phase 1 ---- */
+		/* ---- phase 1: dump-centric walk over the row.  Dump k = np plain chunks + the chunk it ends in
+		   (at sample E); chunks come from the TMA ring, 8 per 128-byte box. ---- */
 		MixAcc acc;
 		acc_zero(acc);
-		int k = 0, widx = 0;
-		for (int b = 0; b < nbox; b++) {
-			const int slot = b % NSTAGE;
-			mbar_wait(smem_u32(bars + slot), (phases >> slot) & 1u);
-			phases ^= 1u << slot;
-			const unsigned char *rowp = stage0 + slot * STAGE_BYTES + lane * 128;
-			const int nchunk = (b == nbox - 1) ? last_chunks : 8;
-			unsigned kinds = c_tab.sched_box[b];	/* one nibble per chunk */
-			/* software pipeline: chunk j+1 is in flight while chunk j is converted and mixed */
-			uint4 vnext = *reinterpret_cast < const uint4 * >(rowp + (l7 << 4));
+		const float4 *dcorr = kp.dcorr + (size_t) ch * VDL2_DUMPS_PER_ROW;
+		int k = 0, widx = 0, bx = 0, j = 0;
+		mbar_wait(smem_u32(bars), phases & 1u);
+		phases ^= 1u;
+		const unsigned char *rowp = stage0 + lane * 128;
+#define VDL2_NEXT_CHUNK()                                                                                  \
+		do {                                                                                        \
+			widx += wpc;                                                                        \
+			widx = (widx == nco) ? 0 : widx;                                                    \
+			if (++j == 8) {                                                                     \
+				j = 0;                                                                      \
+				__syncwarp();                                                               \
+				const int slot_ = bx % NSTAGE;                                              \
+				if (lane == 0 && bx + NSTAGE < nbox) {                                      \
+					const uint32_t bar_ = smem_u32(bars + slot_);                       \
+					mbar_expect_tx(bar_, STAGE_BYTES);                                  \
+					tma_load_3d(smem_u32(stage0 + slot_ * STAGE_BYTES), &tmap, bar_, (bx + NSTAGE) * 32, row0, stream, l2pol); \
+				}                                                                           \
+				bx++;                                                                       \
+				if (bx < nbox) {                                                            \
+					const int ns_ = bx % NSTAGE;                                        \
+					mbar_wait(smem_u32(bars + ns_), (phases >> ns_) & 1u);              \
+					phases ^= 1u << ns_;                                                \
+					rowp = stage0 + ns_ * STAGE_BYTES + lane * 128;                     \
+				}                                                                           \
+			}                                                                                   \
+		} while (0)
 #pragma unroll 1
-			for (int j = 0; j < nchunk; j++) {
-				const uint4 v = vnext;
-				const int jn = j + 1 < nchunk ? j + 1 : j;
-				vnext = *reinterpret_cast < const uint4 * >(rowp + ((jn ^ l7) << 4));
-				const int kind = kinds & 15u;
-				kinds >>= 4;
-				chunk_any < FMT > (kind, acc, v, wsm + widx, sdrow, k);
-				widx += wpc;
-				widx = widx >= nco ? 0 : widx;
+		for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
+			const unsigned sk = c_tab.sched_dump[dk];
+			const int E = (int)(sk >> 8);
+#pragma unroll 1
+			for (int np = (int)(sk & 255u); np > 0; np--) {
+				const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
+				chunk_plain < FMT > (acc, v, wsm + widx, sdrow, dcorr, k);
+				VDL2_NEXT_CHUNK();
 			}
-			__syncwarp();
-			if (lane == 0 && b + NSTAGE < nbox) {
-				const uint32_t bar = smem_u32(bars + slot);
-				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_3d(smem_u32(stage0 + slot * STAGE_BYTES), &tmap, bar, (b + NSTAGE) * 32, row0, stream, l2pol);
-			}
+			const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
+			chunk_bound < FMT > (E, acc, v, wsm + widx, sdrow, dcorr, k);
+			VDL2_NEXT_CHUNK();
 		}
+#undef VDL2_NEXT_CHUNK
 		__threadfence_block();
 		__syncwarp();
 
