@@ -50,8 +50,9 @@ struct Vdl2Tables {
 	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
 	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
 	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
-	unsigned short sched_dump[VDL2_DUMPS_PER_ROW];	/* mixer: per dump of a row, (E << 8) | np: np whole 16-byte chunks, then
-							   the chunk in which the dump ends after sample E */
+	unsigned sched_dump[VDL2_DUMPS_PER_ROW];	/* mixer: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte chunks,
+							   then the chunk in which the dump ends after sample E; w0 = index of
+							   the dump's first chunk in the (extended) oscillator table */
 	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
 };
 
@@ -76,7 +77,8 @@ struct Vdl2KParams {
 	int nrows;		/* rows in this launch (last tile may be short) */
 	int chunks_per_row;	/* row bytes / 16 */
 	int nbox;		/* 128-byte column boxes per row */
-	int nco_pairs;		/* NCO table length in sample pairs */
+	int nco_pairs;		/* NCO table length in float4 entries */
+	int wext;		/* entries appended (copies of the head) so that a dump never wraps */
 	int64_t dump_base;	/* global dump index of row 0 of this launch */
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */

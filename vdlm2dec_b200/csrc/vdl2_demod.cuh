@@ -87,16 +87,21 @@ VQ unsigned revbits(unsigned in, int n)
 
 /* Interpolating low-pass + phase (filteredphase, d8psk.c:219-230) for the dump at tile index d:
    window sd[d .. d+16] (sd carries 16 dumps of history in front), oldest first, taps
-   mflt[clk], mflt[clk+4], ... < 65.  General tap phase; used at the trigger. */
+   mflt[clk], mflt[clk+4], ... < 65.  General tap phase: taps beyond the table are zeros, so the
+   loop always runs 17 taps (x*0 adds nothing), and the 17 L2 loads are issued back to back. */
 VQ float filt_phase_any(const float2 * sd, int d, int clk)
 {
+	float2 x[17];
+#pragma unroll
+	for (int j = 0; j < 17; j++)
+		x[j] = vw::ldcg(sd + d + j);
 	float sr = 0.f, si = 0.f;
-	int j = 0;
-	for (int i = clk; i < VDL2_MFLTLEN; i += 4, j++) {
-		const float m = c_tab.mflt[i];
-		const float2 x = vw::ldcg(sd + d + j);
-		sr = vw::fma(x.x, m, sr);
-		si = vw::fma(x.y, m, si);
+#pragma unroll
+	for (int j = 0; j < 17; j++) {
+		const int i = clk + 4 * j;
+		const float m = c_tab.mflt[i < 67 ? i : 67];	/* entries 63..67 are zero */
+		sr = vw::fma(x[j].x, m, sr);
+		si = vw::fma(x[j].y, m, si);
 	}
 	return vw::atan2(si, sr);
 }

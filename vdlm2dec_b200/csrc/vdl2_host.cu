@@ -36,7 +36,7 @@ struct vdl2gpu {
 	int nstreams;
 	int bytes_per_sample;	/* per IQ sample (or per real sample) */
 	int row_samples, row_bytes, chunks_per_row, nbox, spc;
-	int nco_entries;
+	int nco_entries, wext;
 	int smem, grid, n_sm, ctas_per_sm;
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
@@ -135,8 +135,10 @@ static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
 		if (clk >= (int)h->cfg.sdrclk) {
 			clk %= (int)h->cfg.sdrclk;
 			const int c = n / h->spc, E = n % h->spc;
+			const int wpc = (h->cfg.format == VDL2_FMT_CF32) ? 2 : 4;
+			const int w0 = ((prev_c + 1) * wpc) % h->nco_entries;
 			if (k < VDL2_DUMPS_PER_ROW)
-				t.sched_dump[k] = (unsigned short)((E << 8) | (c - prev_c - 1));
+				t.sched_dump[k] = ((unsigned)w0 << 16) | ((unsigned)E << 8) | (unsigned)(c - prev_c - 1);
 			prev_c = c;
 			k++;
 		}
@@ -218,7 +220,9 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		return fail(NULL, "vdl2_create: constant table upload failed: %s", cudaGetErrorString(e));
 	}
 
-	h->smem = vdl2_kernel_smem_bytes(h->nco_entries);
+	/* longest dump in chunks (+1 boundary chunk) times entries per chunk: how far past the table a dump can read */
+	h->wext = ((int)((cfg->fs / 84000 + 2 + h->spc - 1) / h->spc) + 1) * ((cfg->format == VDL2_FMT_CF32) ? 2 : 4);
+	h->smem = vdl2_kernel_smem_bytes(h->nco_entries + h->wext);
 	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->smem, &h->ctas_per_sm);
 	if (e != cudaSuccess || h->ctas_per_sm < 1) {
 		delete h;
@@ -410,6 +414,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.chunks_per_row = h->chunks_per_row;
 	kp.nbox = h->nbox;
 	kp.nco_pairs = h->nco_entries;
+	kp.wext = h->wext;
 	kp.dump_base = h->rows_done * VDL2_DUMPS_PER_ROW;
 	kp.state = h->d_state;
 	kp.wtab = h->d_wtab;

@@ -278,8 +278,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	const int nitems = kp.ntiles * kp.nch;
 	const int wpc = FmtTraits < FMT >::wper_chunk;
 	const int nbox = kp.nbox;
-	int nco = kp.nco_pairs;
-	asm volatile ("":"+r" (nco));	/* keep the wrap limit in a register (ptxas otherwise reloads the parameter per chunk) */
+	const int nco = kp.nco_pairs;
 	unsigned long long l2pol;	/* the input is read exactly once: evict-first keeps the per-warp scratch L2 resident */
 	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
 	const uint32_t l7 = (uint32_t) (lane & 7);
@@ -307,23 +306,23 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream, l2pol);
 			}
 		}
-		for (int i = lane; i < nco; i += 32)
-			wsm[i] = kp.wtab[(size_t) ch * nco + i];
+		for (int i = lane; i < nco + kp.wext; i += 32)
+			wsm[i] = kp.wtab[(size_t) ch * nco + (i < nco ? i : i - nco)];
 		__syncwarp();
 
 		/* ---- phase 1: dump-centric walk over the row.  Dump k = np plain chunks + the chunk it ends in
-		   (at sample E); chunks come from the TMA ring, 8 per 128-byte box. ---- */
+		   (after sample E); chunks come from the TMA ring, 8 per 128-byte box; the oscillator table is
+		   addressed from a per-dump base (no wrap inside a dump: the table is extended). ---- */
 		MixAcc acc;
 		acc_zero(acc);
 		const float4 *dcorr = kp.dcorr + (size_t) ch * VDL2_DUMPS_PER_ROW;
-		int k = 0, widx = 0, bx = 0, j = 0;
+		int k = 0, bx = 0, j = 0;
 		mbar_wait(smem_u32(bars), phases & 1u);
 		phases ^= 1u;
 		const unsigned char *rowp = stage0 + lane * 128;
+#define VDL2_LOAD_CHUNK() (*reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4)))
 #define VDL2_NEXT_CHUNK()                                                                                  \
 		do {                                                                                        \
-			widx += wpc;                                                                        \
-			widx = (widx == nco) ? 0 : widx;                                                    \
 			if (++j == 8) {                                                                     \
 				j = 0;                                                                      \
 				__syncwarp();                                                               \
@@ -345,18 +344,32 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 #pragma unroll 1
 		for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
 			const unsigned sk = c_tab.sched_dump[dk];
-			const int E = (int)(sk >> 8);
-#pragma unroll 1
-			for (int np = (int)(sk & 255u); np > 0; np--) {
-				const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
-				chunk_plain < FMT > (acc, v, wsm + widx, sdrow, dcorr, k);
+			const int E = (int)((sk >> 8) & 255u);
+			const float4 *w = wsm + (sk >> 16);
+			int np = (int)(sk & 255u);
+			if (np == 2) {	/* the common shape at 2 Msps: 24 (23) samples = 2 whole chunks + the boundary chunk */
+				uint4 v = VDL2_LOAD_CHUNK();
+				chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
 				VDL2_NEXT_CHUNK();
+				v = VDL2_LOAD_CHUNK();
+				chunk_plain < FMT > (acc, v, w + wpc, sdrow, dcorr, k);
+				VDL2_NEXT_CHUNK();
+				w += 2 * wpc;
+			} else {
+#pragma unroll 1
+				for (; np > 0; np--) {
+					const uint4 v = VDL2_LOAD_CHUNK();
+					chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
+					VDL2_NEXT_CHUNK();
+					w += wpc;
+				}
 			}
-			const uint4 v = *reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4));
-			chunk_bound < FMT > (E, acc, v, wsm + widx, sdrow, dcorr, k);
+			const uint4 v = VDL2_LOAD_CHUNK();
+			chunk_bound < FMT > (E, acc, v, w, sdrow, dcorr, k);
 			VDL2_NEXT_CHUNK();
 		}
 #undef VDL2_NEXT_CHUNK
+#undef VDL2_LOAD_CHUNK
 		__threadfence_block();
 		__syncwarp();
 
