@@ -10,9 +10,9 @@ from vdlm2dec_b200 import synth
 D_TOL = 1e-5  # rad, absolute: the north_star's soft-symbol tolerance (DESIGN.md "numerics")
 
 
-def make_channels(nch, nsamples, seed=1, fs=2_000_000, fmt="cu8", period=60000, **kw):
+def make_channels(nch, nsamples, seed=1, fs=2_000_000, fmt="cu8", period=60000, fos=None, **kw):
     """nch independent streams; Fo cycles over the legal 25 kHz raster (|Fo| >= 50 kHz)."""
-    fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+    fos = fos or [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
     specs, iqs = [], []
     for c in range(nch):
         spec = synth.standard_channel(seed=seed * 1000 + c, nsamples=nsamples, Fo=fos[c % len(fos)], fs=fs,

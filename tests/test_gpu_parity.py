@@ -46,6 +46,32 @@ def test_parity_formats(fmt, screen):
     assert g.stats()["kernel_launches"] == 1
 
 
+@pytest.mark.parametrize("fmt,fs,sdrclk,fos", [
+    ("cs16", 2_000_000, 500, None),
+    ("cs16", 10_000_000, 2500, [-2_450_000, 1_175_000, 3_300_000, -50_000]),   # BASELINE config 5 shape (extension)
+    ("f32real", 6_000_000, 1500, [1_250_000, 1_500_000 - 125_000, 2_100_000]),  # Airspy 6 Msps real (air.c:37-38)
+    ("f32real", 5_000_000, 1250, [1_000_000, 1_250_000 + 75_000]),              # Airspy 5 Msps real (air.c:134-138)
+])
+def test_parity_other_rates_and_formats(fmt, fs, sdrclk, fos):
+    """cs16 and the Airspy real-sample mode at their own rates: the row is still 1 ms (fs/1000 samples,
+    84 dumps), only the dump schedule, the NCO period (fs/25 kHz) and the chunk decoding change."""
+    nch = len(fos) if fos else 4
+    n = fs // 1000 * 450
+    specs, iq = make_channels(nch, n, seed=13, fs=fs, fmt=fmt, fos=fos, period=int(0.03 * fs))
+    g = Vdl2Gpu([(c, 136_975_000, specs[c].Fo) for c in range(nch)], fs=fs, sdrclk=sdrclk, fmt=fmt, taps=SCREEN_TAPS,
+                max_samples=n)
+    g.process(iq)
+    blocks = g.drain_blocks()
+    total = 0
+    for c, spec in enumerate(specs):
+        o = Oracle("port", chn=c, Fo=spec.Fo, fs=fs, sdrclk=sdrclk).feed(iq[c], fmt)
+        gd = g.read_dumps(c)
+        assert len(gd) == n // (fs // 1000) * 84
+        rep = compare_channel(o, blocks[blocks["chn"] == c], g.read_syncs(c), g.read_syms(c), gd, None, ndump_limit=len(gd))
+        total += rep["blocks"][0]
+    assert total >= nch
+
+
 def test_parity_streaming_rtl_blocks():
     """65536-byte callbacks (rtl.c:302): 32768 samples is not a whole number of 1 ms rows, so the
     sub-row tail is carried between calls like the reference carries clk/nf/no (d8psk.c:343-347)."""

@@ -135,7 +135,7 @@ static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
 		if (clk >= (int)h->cfg.sdrclk) {
 			clk %= (int)h->cfg.sdrclk;
 			const int c = n / h->spc, E = n % h->spc;
-			const int wpc = (h->cfg.format == VDL2_FMT_CF32) ? 2 : 4;
+			const int wpc = (h->spc == 8) ? 4 : 2;
 			const int w0 = ((prev_c + 1) * wpc) % h->nco_entries;
 			if (k < VDL2_DUMPS_PER_ROW)
 				t.sched_dump[k] = ((unsigned)w0 << 16) | ((unsigned)E << 8) | (unsigned)(c - prev_c - 1);
@@ -152,8 +152,8 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	*out = NULL;
 	if (cfg->nch <= 0 || cfg->ch_per_stream <= 0 || cfg->nch % cfg->ch_per_stream)
 		return fail(NULL, "vdl2_create: nch=%d must be a positive multiple of ch_per_stream=%d", cfg->nch, cfg->ch_per_stream);
-	if (cfg->format != VDL2_FMT_CU8 && cfg->format != VDL2_FMT_CS8 && cfg->format != VDL2_FMT_CF32)
-		return fail(NULL, "vdl2_create: format %d not built into this library (cu8, cs8, cf32 are)", cfg->format);
+	if (cfg->format < VDL2_FMT_CU8 || cfg->format > VDL2_FMT_F32REAL)
+		return fail(NULL, "vdl2_create: unknown sample format %d", cfg->format);
 	if (cfg->fs % 1000 || cfg->fs % VDL2_STEPRATE || cfg->sdrclk == 0 || (cfg->fs / 1000 * 21) % cfg->sdrclk)
 		return fail(NULL, "vdl2_create: fs=%u / sdrclk=%u do not give a 1 ms joint period", cfg->fs, cfg->sdrclk);
 	int ndev = 0;
@@ -221,7 +221,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	}
 
 	/* longest dump in chunks (+1 boundary chunk) times entries per chunk: how far past the table a dump can read */
-	h->wext = ((int)((cfg->fs / 84000 + 2 + h->spc - 1) / h->spc) + 1) * ((cfg->format == VDL2_FMT_CF32) ? 2 : 4);
+	h->wext = ((int)((cfg->fs / 84000 + 2 + h->spc - 1) / h->spc) + 1) * ((h->spc == 8) ? 4 : 2);
 	h->smem = vdl2_kernel_smem_bytes(h->nco_entries + h->wext);
 	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->smem, &h->ctas_per_sm);
 	if (e != cudaSuccess || h->ctas_per_sm < 1) {

@@ -114,6 +114,9 @@ template < int FMT > __device__ __forceinline__ void dump_close(MixAcc & a, floa
 	if (FMT == VDL2_FMT_CF32) {
 		re = a.A.x - a.C.y;
 		im = a.C.x + a.A.y;
+	} else if (FMT == VDL2_FMT_F32REAL) {
+		re = a.A.x + a.A.y;
+		im = a.C.x + a.C.y;
 	} else {
 		re = (a.A.x + a.A.y) - (a.B.x + a.B.y);
 		im = (a.C.x + a.C.y) + (a.G.x + a.G.y);
@@ -206,10 +209,75 @@ template < int E > __device__ __forceinline__ void chunk_cf32(MixAcc & a, uint4 
 		dump_close < VDL2_FMT_CF32 > (a, sdrow, dcorr, k);
 }
 
+/* signed 16-bit IQ: a chunk is 4 samples = 2 pairs.  Sign bit flipped, PRMT builds 2^23 + u16,
+   one packed add removes 2^23 + 32768: exact. */
+__device__ __forceinline__ void cvt_pair16(uint32_t w0, uint32_t w1, float2 & xr, float2 & xi)
+{
+	w0 ^= 0x80008000u;
+	w1 ^= 0x80008000u;
+	const uint32_t magic = 0x4B000000u;
+	xr.x = __uint_as_float(__byte_perm(w0, magic, 0x7410));
+	xi.x = __uint_as_float(__byte_perm(w0, magic, 0x7432));
+	xr.y = __uint_as_float(__byte_perm(w1, magic, 0x7410));
+	xi.y = __uint_as_float(__byte_perm(w1, magic, 0x7432));
+	const float2 m = make_float2(-8421376.f, -8421376.f);	/* -(2^23 + 2^15) */
+	xr = fadd2(xr, m);
+	xi = fadd2(xi, m);
+}
+
+/* real samples (Airspy, air.c:206-208 + d8psk.c:368 with a float Cbuff): D += x * w */
+template < int SPLIT > __device__ __forceinline__ void mac_pair_real(MixAcc & a, float2 x, float4 W, float2 * sdrow, const float4 * dcorr,
+								      int &k)
+{
+	if (SPLIT == 1) {
+		a.A.x = fmaf(x.x, W.x, a.A.x);
+		a.C.x = fmaf(x.x, W.z, a.C.x);
+		dump_close < VDL2_FMT_F32REAL > (a, sdrow, dcorr, k);
+		a.A.y = x.y * W.y;
+		a.C.y = x.y * W.w;
+	} else {
+		a.A = ffma2(x, make_float2(W.x, W.y), a.A);
+		a.C = ffma2(x, make_float2(W.z, W.w), a.C);
+		if (SPLIT == 2)
+			dump_close < VDL2_FMT_F32REAL > (a, sdrow, dcorr, k);
+	}
+}
+
+/* a 16-byte chunk of 4 samples (cs16 IQ or float32 real) = 2 pairs; E as in chunk8, 4 = none */
+template < int FMT, int E > __device__ __forceinline__ void chunk4(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								    const float4 * dcorr, int &k)
+{
+	const uint32_t d[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+	for (int p = 0; p < 2; p++) {
+		const float4 W = w[p];
+		if (FMT == VDL2_FMT_F32REAL) {
+			const float2 x = make_float2(__uint_as_float(d[2 * p]), __uint_as_float(d[2 * p + 1]));
+			if (E == 2 * p)
+				mac_pair_real < 1 > (a, x, W, sdrow, dcorr, k);
+			else if (E == 2 * p + 1)
+				mac_pair_real < 2 > (a, x, W, sdrow, dcorr, k);
+			else
+				mac_pair_real < 0 > (a, x, W, sdrow, dcorr, k);
+		} else {
+			float2 xr, xi;
+			cvt_pair16(d[2 * p], d[2 * p + 1], xr, xi);
+			if (E == 2 * p)
+				mac_pair < FMT, 1 > (a, xr, xi, W, sdrow, dcorr, k);
+			else if (E == 2 * p + 1)
+				mac_pair < FMT, 2 > (a, xr, xi, W, sdrow, dcorr, k);
+			else
+				mac_pair < FMT, 0 > (a, xr, xi, W, sdrow, dcorr, k);
+		}
+	}
+}
+
 template < int FMT > struct FmtTraits;
 template <> struct FmtTraits <VDL2_FMT_CU8 > { static constexpr int wper_chunk = 4, spc = 8; };
 template <> struct FmtTraits <VDL2_FMT_CS8 > { static constexpr int wper_chunk = 4, spc = 8; };
 template <> struct FmtTraits <VDL2_FMT_CF32 > { static constexpr int wper_chunk = 2, spc = 2; };
+template <> struct FmtTraits <VDL2_FMT_CS16 > { static constexpr int wper_chunk = 2, spc = 4; };
+template <> struct FmtTraits <VDL2_FMT_F32REAL > { static constexpr int wper_chunk = 2, spc = 4; };
 
 /* a chunk the current dump runs straight through */
 template < int FMT > __device__ __forceinline__ void chunk_plain(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
@@ -217,6 +285,8 @@ template < int FMT > __device__ __forceinline__ void chunk_plain(MixAcc & a, uin
 {
 	if (FMT == VDL2_FMT_CF32)
 		chunk_cf32 < 2 > (a, v, w, sdrow, dcorr, k);
+	else if (FMT == VDL2_FMT_CS16 || FMT == VDL2_FMT_F32REAL)
+		chunk4 < FMT, 4 > (a, v, w, sdrow, dcorr, k);
 	else
 		chunk8 < FMT, 8 > (a, v, w, sdrow, dcorr, k);
 }
@@ -230,6 +300,13 @@ template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc &
 			chunk_cf32 < 0 > (a, v, w, sdrow, dcorr, k);
 		else
 			chunk_cf32 < 1 > (a, v, w, sdrow, dcorr, k);
+	} else if (FMT == VDL2_FMT_CS16 || FMT == VDL2_FMT_F32REAL) {
+		switch (E) {
+		case 0: chunk4 < FMT, 0 > (a, v, w, sdrow, dcorr, k); break;
+		case 1: chunk4 < FMT, 1 > (a, v, w, sdrow, dcorr, k); break;
+		case 2: chunk4 < FMT, 2 > (a, v, w, sdrow, dcorr, k); break;
+		default: chunk4 < FMT, 3 > (a, v, w, sdrow, dcorr, k); break;
+		}
 	} else {
 		switch (E) {
 		case 0: chunk8 < FMT, 0 > (a, v, w, sdrow, dcorr, k); break;
@@ -490,30 +567,28 @@ extern "C" int vdl2_kernel_launch(int fmt, const void *tmap, const Vdl2KParams *
 	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8 > (m, *kp, grid, smem, st);
 	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8 > (m, *kp, grid, smem, st);
 	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL > (m, *kp, grid, smem, st);
 	}
 	return (int)cudaErrorInvalidValue;
 }
 
+template < int FMT > static cudaError_t occ_fmt(int smem, int *n)
+{
+	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, vdl2::vdl2_frontend_kernel < FMT >, 32, smem);
+}
+
 extern "C" int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm)
 {
-	cudaError_t e;
 	switch (fmt) {
-	case VDL2_FMT_CU8:
-		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CU8 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CU8 >, 32, smem);
-		break;
-	case VDL2_FMT_CS8:
-		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CS8 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CS8 >, 32, smem);
-		break;
-	case VDL2_FMT_CF32:
-		cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < VDL2_FMT_CF32 >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vdl2::vdl2_frontend_kernel < VDL2_FMT_CF32 >, 32, smem);
-		break;
-	default:
-		return (int)cudaErrorInvalidValue;
+	case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8 > (smem, ctas_per_sm);
+	case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8 > (smem, ctas_per_sm);
+	case VDL2_FMT_CF32: return (int)occ_fmt < VDL2_FMT_CF32 > (smem, ctas_per_sm);
+	case VDL2_FMT_CS16: return (int)occ_fmt < VDL2_FMT_CS16 > (smem, ctas_per_sm);
+	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL > (smem, ctas_per_sm);
 	}
-	return (int)e;
+	return (int)cudaErrorInvalidValue;
 }
 
 extern "C" int vdl2_kernel_upload_tables(const Vdl2Tables * t)

@@ -299,6 +299,8 @@ def quantise(x: np.ndarray, fmt: str) -> np.ndarray:
         return np.clip(np.rint(iq * 128.0), -32768, 32767).astype(np.int16)
     if fmt == "cf32":
         return iq.astype(np.float32)
+    if fmt == "f32real":  # Airspy AIRSPY_SAMPLE_FLOAT32_REAL (air.c:123): real samples, full scale ~1
+        return (x.real / 64.0).astype(np.float32)
     raise ValueError(fmt)
 
 
