@@ -17,7 +17,7 @@ from typing import Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvdl2gpu.so")
+LIB_PATH = os.environ.get("VDL2_LIB") or os.path.join(HERE, "libvdl2gpu.so")  # VDL2_LIB: experimental variants (tools/)
 
 FORMATS = {"cu8": 0, "cs8": 1, "cs16": 2, "cf32": 3, "f32real": 4}
 FMT_DTYPE = {"cu8": np.uint8, "cs8": np.int8, "cs16": np.int16, "cf32": np.float32, "f32real": np.float32}

@@ -22,23 +22,28 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: str | None = None) -> str:
+    """defines/out build an experimental variant next to the product library (tools/ab_probe.py)."""
+    lib = LIB if out is None else os.path.join(HERE, out)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    if not force and not _stale(LIB, deps):
-        return LIB
+    if not force and not _stale(lib, deps):
+        return lib
     objs = []
+    tag = "" if out is None else "." + os.path.splitext(out)[0]
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(CSRC, s.replace(".cu", tag + ".o"))
+        cmd = [NVCC, *ARCH, *FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
         objs.append(o)
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
+    cmd = [NVCC, *ARCH, "-shared", "-o", lib, *objs]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

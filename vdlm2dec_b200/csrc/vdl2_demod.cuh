@@ -91,6 +91,17 @@ VQ unsigned revbits(unsigned in, int n)
    loop always runs 17 taps (x*0 adds nothing), and the 17 L2 loads are issued back to back. */
 VQ float filt_phase_any(const float2 * sd, int d, int clk)
 {
+#ifdef VDL2_OLD_FILT
+	float sr0 = 0.f, si0 = 0.f;
+	int jj = 0;
+	for (int i = clk; i < VDL2_MFLTLEN; i += 4, jj++) {
+		const float m = c_tab.mflt[i];
+		const float2 x = vw::ldcg(sd + d + jj);
+		sr0 = vw::fma(x.x, m, sr0);
+		si0 = vw::fma(x.y, m, si0);
+	}
+	return vw::atan2(si0, sr0);
+#endif
 	float2 x[17];
 #pragma unroll
 	for (int j = 0; j < 17; j++)

@@ -322,7 +322,7 @@ template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc &
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template < int FMT > __global__ void __launch_bounds__(32, 16)
+template < int FMT > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
 vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
@@ -424,6 +424,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			const int E = (int)((sk >> 8) & 255u);
 			const float4 *w = wsm + (sk >> 16);
 			int np = (int)(sk & 255u);
+#ifdef VDL2_UNROLL_NP2
 			if (np == 2) {	/* the common shape at 2 Msps: 24 (23) samples = 2 whole chunks + the boundary chunk */
 				uint4 v = VDL2_LOAD_CHUNK();
 				chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
@@ -432,7 +433,9 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 				chunk_plain < FMT > (acc, v, w + wpc, sdrow, dcorr, k);
 				VDL2_NEXT_CHUNK();
 				w += 2 * wpc;
-			} else {
+			} else
+#endif
+			{
 #pragma unroll 1
 				for (; np > 0; np--) {
 					const uint4 v = VDL2_LOAD_CHUNK();

@@ -4,7 +4,12 @@
 #include "../../include/vdl2gpu.h"
 #include "vdl2_common.h"
 
-#define VDL2_NSTAGE 3		/* TMA boxes (32 rows x 128 B) in flight per warp */
+#ifndef VDL2_NSTAGE
+#define VDL2_NSTAGE 3
+#endif
+#ifndef VDL2_MIN_CTAS
+#define VDL2_MIN_CTAS 16
+#endif		/* TMA boxes (32 rows x 128 B) in flight per warp */
 
 #ifdef __cplusplus
 extern "C" {
