@@ -16,6 +16,7 @@
 #include <vector_functions.h>
 
 #define VQ static inline
+#define VQ_COLD static
 #define VDL2_CONST
 
 namespace vw {

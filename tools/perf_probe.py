@@ -10,12 +10,17 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 cps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 ns = ns // 2000 * 2000
 nstreams = nch // cps
+bursts = len(sys.argv) > 5 and sys.argv[5] == "bursts"
 x = torch.empty((nstreams, ns * 2), dtype=torch.uint8, device="cuda")
-for s0 in range(0, nstreams, 64):  # gaussian-ish noise around 127, generated in slices to bound memory
+if bursts:
+    from vdlm2dec_b200.synth_torch import make_device_workload
+    x, fos_b, nb = make_device_workload(nstreams, ns, seed=1000, device=torch.device("cuda"))
+    print("bursts placed", nb)
+for s0 in range(0, 0 if bursts else nstreams, 64):  # gaussian-ish noise around 127, generated in slices to bound memory
     sl = x[s0:s0 + 64]
     sl.copy_(((torch.randint(0, 256, sl.shape, device="cuda").float() + torch.randint(0, 256, sl.shape, device="cuda").float()) * 0.0625 + 111.0).to(torch.uint8))
 fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
-chans = [(c, 136_975_000, fos[c % len(fos)]) for c in range(nch)]
+chans = [(c, 136_975_000, fos_b[c] if bursts else fos[c % len(fos)]) for c in range(nch)]
 g = Vdl2Gpu(chans, ch_per_stream=cps, max_samples=ns)
 torch.cuda.synchronize()
 for r in range(reps):

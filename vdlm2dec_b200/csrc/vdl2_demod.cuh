@@ -33,6 +33,7 @@
 
 #ifdef __CUDACC__
 #define VQ __device__ __forceinline__
+#define VQ_COLD __device__ __noinline__	/* rare paths: kept out of line so the hot loops stay I-cache resident */
 #define VDL2_CONST __constant__
 namespace vw {
 VQ int lane() { return threadIdx.x & 31; }
@@ -119,7 +120,7 @@ VQ float filt_phase_any(const float2 * sd, int d, int clk)
 
 /* 17-point least-squares line through the unwrapped (phase - unique word) sequence
    (d8psk.c:259-289).  ph[4*l] is the phase of symbol l.  Returns residual and slope. */
-VQ void sync_fit(const float *ph, float &err_out, float &fr_out)
+VQ_COLD float2 sync_fit_nv(const float *ph)
 {
 	float Pr[VDL2_NBPH];
 	float kf = 0.f, Pv, M;
@@ -151,8 +152,14 @@ VQ void sync_fit(const float *ph, float &err_out, float &fr_out)
 		const float e = vw::fma(-(float)(l - 8), fr, Pr[l]);
 		err = vw::fma(e, e, err);
 	}
-	err_out = err;
-	fr_out = fr;
+	return make_float2(err, fr);
+}
+
+VQ void sync_fit(const float *ph, float &err_out, float &fr_out)
+{
+	const float2 r = sync_fit_nv(ph);
+	err_out = r.x;
+	fr_out = r.y;
 }
 
 /* burst geometry from the header (d8psk.c:94-95, :139-162, :188-197) */
@@ -216,7 +223,7 @@ VQ int byte_slot(const BurstGeom & g, int B)
 /* 25-bit header through the 32-state max-product trellis, lane = state (viterbi.c:37-96).
    The update order of the reference (ascending source state, '1' branch before '0') decides
    ties; it is reproduced by ordering the two candidates of a target state by source index. */
-VQ unsigned header_decode(const float *hv)
+VQ_COLD unsigned header_decode(const float *hv)
 {
 	const int s = vw::lane();
 	double pb = (s == 0) ? 1.0 : 0.0;

@@ -172,22 +172,41 @@ template < int FMT, int SPLIT > __device__ __forceinline__ void mac_pair(MixAcc 
 
 /* a 16-byte chunk of 8-bit IQ = 8 samples = 4 pairs; E = last sample of the current dump
    inside this chunk (0..7), or 8 if the dump continues through the whole chunk */
-template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
-								    const float4 * dcorr, int &k)
+struct Pairs8 {
+	float2 xr[4], xi[4];
+	float4 W[4];
+};
+
+template < int FMT > __device__ __forceinline__ void load_pairs8(Pairs8 & P, uint4 v, const float4 * w)
 {
 	const uint32_t d[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
 	for (int p = 0; p < 4; p++) {
-		float2 xr, xi;
-		cvt_pair8 < FMT > (d[p], xr, xi);
-		const float4 W = w[p];
-		if (E == 2 * p)
-			mac_pair < FMT, 1 > (a, xr, xi, W, sdrow, dcorr, k);
-		else if (E == 2 * p + 1)
-			mac_pair < FMT, 2 > (a, xr, xi, W, sdrow, dcorr, k);
-		else
-			mac_pair < FMT, 0 > (a, xr, xi, W, sdrow, dcorr, k);
+		cvt_pair8 < FMT > (d[p], P.xr[p], P.xi[p]);
+		P.W[p] = w[p];
 	}
+}
+
+template < int FMT, int E > __device__ __forceinline__ void mac_pairs8(MixAcc & a, const Pairs8 & P, float2 * sdrow, const float4 * dcorr,
+									int &k)
+{
+#pragma unroll
+	for (int p = 0; p < 4; p++) {
+		if (E == 2 * p)
+			mac_pair < FMT, 1 > (a, P.xr[p], P.xi[p], P.W[p], sdrow, dcorr, k);
+		else if (E == 2 * p + 1)
+			mac_pair < FMT, 2 > (a, P.xr[p], P.xi[p], P.W[p], sdrow, dcorr, k);
+		else
+			mac_pair < FMT, 0 > (a, P.xr[p], P.xi[p], P.W[p], sdrow, dcorr, k);
+	}
+}
+
+template < int FMT, int E > __device__ __forceinline__ void chunk8(MixAcc & a, uint4 v, const float4 * w, float2 * sdrow,
+								    const float4 * dcorr, int &k)
+{
+	Pairs8 P;
+	load_pairs8 < FMT > (P, v, w);
+	mac_pairs8 < FMT, E > (a, P, sdrow, dcorr, k);
 }
 
 /* complex float input (the reference's Cbuff, vdlm2.h:89): a chunk is 2 samples; the oscillator
@@ -308,15 +327,18 @@ template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc &
 		default: chunk4 < FMT, 3 > (a, v, w, sdrow, dcorr, k); break;
 		}
 	} else {
+		/* conversions and oscillator loads are common to the eight boundary positions */
+		Pairs8 P;
+		load_pairs8 < FMT > (P, v, w);
 		switch (E) {
-		case 0: chunk8 < FMT, 0 > (a, v, w, sdrow, dcorr, k); break;
-		case 1: chunk8 < FMT, 1 > (a, v, w, sdrow, dcorr, k); break;
-		case 2: chunk8 < FMT, 2 > (a, v, w, sdrow, dcorr, k); break;
-		case 3: chunk8 < FMT, 3 > (a, v, w, sdrow, dcorr, k); break;
-		case 4: chunk8 < FMT, 4 > (a, v, w, sdrow, dcorr, k); break;
-		case 5: chunk8 < FMT, 5 > (a, v, w, sdrow, dcorr, k); break;
-		case 6: chunk8 < FMT, 6 > (a, v, w, sdrow, dcorr, k); break;
-		default: chunk8 < FMT, 7 > (a, v, w, sdrow, dcorr, k); break;
+		case 0: mac_pairs8 < FMT, 0 > (a, P, sdrow, dcorr, k); break;
+		case 1: mac_pairs8 < FMT, 1 > (a, P, sdrow, dcorr, k); break;
+		case 2: mac_pairs8 < FMT, 2 > (a, P, sdrow, dcorr, k); break;
+		case 3: mac_pairs8 < FMT, 3 > (a, P, sdrow, dcorr, k); break;
+		case 4: mac_pairs8 < FMT, 4 > (a, P, sdrow, dcorr, k); break;
+		case 5: mac_pairs8 < FMT, 5 > (a, P, sdrow, dcorr, k); break;
+		case 6: mac_pairs8 < FMT, 6 > (a, P, sdrow, dcorr, k); break;
+		default: mac_pairs8 < FMT, 7 > (a, P, sdrow, dcorr, k); break;
 		}
 	}
 }
