@@ -72,6 +72,25 @@ def test_parity_other_rates_and_formats(fmt, fs, sdrclk, fos):
     assert total >= nch
 
 
+def test_two_handles_with_different_rates_interleaved():
+    """Handles are independent: a 2 Msps cu8 handle and a 6 Msps Airspy-real handle fed alternately
+    (the rate/format dependent dump schedule is per handle, not a shared constant)."""
+    na, nb = 600_000, 1_800_000
+    sa, ia = make_channels(2, na, seed=31)
+    sb, ib = make_channels(2, nb, seed=32, fs=6_000_000, fmt="f32real", fos=[1_250_000, 2_100_000], period=180_000)
+    a = Vdl2Gpu([(c, 136_975_000, sa[c].Fo) for c in range(2)], taps=SCREEN_TAPS, max_samples=na)
+    b = Vdl2Gpu([(c, 136_975_000, sb[c].Fo) for c in range(2)], fs=6_000_000, sdrclk=1500, fmt="f32real", taps=SCREEN_TAPS, max_samples=nb)
+    for k in range(3):
+        a.process(ia[:, k * 2 * (na // 3):(k + 1) * 2 * (na // 3)])
+        b.process(ib[:, k * (nb // 3):(k + 1) * (nb // 3)])
+    _check_all(a, sa, ia, "cu8", steps=False)
+    blocks = b.drain_blocks()
+    for c, spec in enumerate(sb):
+        o = Oracle("port", chn=c, Fo=spec.Fo, fs=6_000_000, sdrclk=1500).feed(ib[c], "f32real")
+        gd = b.read_dumps(c)
+        compare_channel(o, blocks[blocks["chn"] == c], b.read_syncs(c), b.read_syms(c), gd, None, ndump_limit=len(gd))
+
+
 def test_parity_streaming_rtl_blocks():
     """65536-byte callbacks (rtl.c:302): 32768 samples is not a whole number of 1 ms rows, so the
     sub-row tail is carried between calls like the reference carries clk/nf/no (d8psk.c:343-347)."""

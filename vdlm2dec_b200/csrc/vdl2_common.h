@@ -44,15 +44,12 @@ struct Vdl2ChanState {
 	int32_t pad[6];
 };
 
-/* constant tables of the kernel */
+/* constant tables of the kernel (independent of rate and format, so handles can share them) */
 struct Vdl2Tables {
 	float mflt[68];		/* interpolating low-pass taps, 65 used (d8psk.h:28-45) */
 	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
 	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
 	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
-	unsigned sched_dump[VDL2_DUMPS_PER_ROW];	/* mixer: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte chunks,
-							   then the chunk in which the dump ends after sample E; w0 = index of
-							   the dump's first chunk in the (extended) oscillator table */
 	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
 };
 
@@ -83,6 +80,9 @@ struct Vdl2KParams {
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
 	const float4 *dcorr;	/* [nch][84]: per dump (1/nf, 1/nf, -cre/nf, -cim/nf), see dump_close */
+	const unsigned *sched;	/* [84]: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte chunks, then the
+				   chunk in which the dump ends after sample E; w0 = index of the dump's first chunk in the
+				   (extended) oscillator table.  Per handle: it depends on fs, SDRCLK and the sample format */
 	unsigned *ticket;	/* work counter */
 	int *progress;		/* [nch]: tiles completed in this launch */
 	uint8_t *curblk;	/* [nch][2048] block under construction */

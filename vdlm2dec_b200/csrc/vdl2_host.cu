@@ -45,6 +45,7 @@ struct vdl2gpu {
 	Vdl2ChanState *d_state;
 	float4 *d_wtab;
 	float4 *d_dcorr;
+	unsigned *d_sched;
 	unsigned *d_ticket;
 	int *d_progress;
 	uint8_t *d_curblk;
@@ -104,7 +105,7 @@ static int fmt_bytes(int fmt)
 	return 0;
 }
 
-static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
+static void build_tables(Vdl2Tables & t, unsigned *sched_dump, const vdl2gpu * h)
 {
 	memset(&t, 0, sizeof t);
 	float mf[VDL2_MFLTLEN], sw[VDL2_NBPH];
@@ -138,7 +139,7 @@ static void build_tables(Vdl2Tables & t, const vdl2gpu * h)
 			const int wpc = (h->spc == 8) ? 4 : 2;
 			const int w0 = ((prev_c + 1) * wpc) % h->nco_entries;
 			if (k < VDL2_DUMPS_PER_ROW)
-				t.sched_dump[k] = ((unsigned)w0 << 16) | ((unsigned)E << 8) | (unsigned)(c - prev_c - 1);
+				sched_dump[k] = ((unsigned)w0 << 16) | ((unsigned)E << 8) | (unsigned)(c - prev_c - 1);
 			prev_c = c;
 			k++;
 		}
@@ -212,7 +213,8 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	}
 
 	Vdl2Tables *tab = new Vdl2Tables();
-	build_tables(*tab, h);
+	unsigned sched_dump[VDL2_DUMPS_PER_ROW];
+	build_tables(*tab, sched_dump, h);
 	e = (cudaError_t) vdl2_kernel_upload_tables(tab);
 	delete tab;
 	if (e != cudaSuccess) {
@@ -308,6 +310,8 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
 	}
 
+	CK(h, cudaMalloc(&h->d_sched, sizeof sched_dump));
+	CK(h, cudaMemcpy(h->d_sched, sched_dump, sizeof sched_dump, cudaMemcpyHostToDevice));
 	CK(h, cudaMalloc(&h->d_ticket, 64));
 	CK(h, cudaMemset(h->d_ticket, 0, 64));
 	h->d_outq_count = h->d_ticket + 4;
@@ -366,6 +370,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
+	cudaFree(h->d_sched);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_curblk);
@@ -419,6 +424,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.state = h->d_state;
 	kp.wtab = h->d_wtab;
 	kp.dcorr = h->d_dcorr;
+	kp.sched = h->d_sched;
 	kp.ticket = h->d_ticket;
 	kp.progress = h->d_progress;
 	kp.curblk = h->d_curblk;

@@ -442,7 +442,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		} while (0)
 #pragma unroll 1
 		for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
-			const unsigned sk = c_tab.sched_dump[dk];
+			const unsigned sk = __ldg(kp.sched + dk);
 			const int E = (int)((sk >> 8) & 255u);
 			const float4 *w = wsm + (sk >> 16);
 			int np = (int)(sk & 255u);
