@@ -16,6 +16,7 @@
 #define VDL2_HIST 16		/* dumps of history in front of a tile (MBUFLEN-1) */
 #define VDL2_PHHIST 64		/* idle-mode phases of history ((NBPH-1)*D8DWN) */
 #define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
+#define VDL2_SCHED_SLOTS 8	/* distinct (fs, SDRCLK, format) combinations alive in one process */
 #define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
 
 #define VDL2_FLAG_NO_SCREEN 1u	/* debug: run the exact 17-point fit at every idle step */
@@ -50,6 +51,8 @@ struct Vdl2Tables {
 	float sync[20];		/* unique-word phases, 17 used (d8psk.h:20-26) */
 	float soft[3][260];	/* soft demap, 257 used per bit (d8psk.h:47-249) */
 	unsigned scr[VDL2_SCR_WORDS];	/* descrambler bit sequence from seed 0x4D4B (d8psk.c:54-65,299) */
+	unsigned sched_slots[VDL2_SCHED_SLOTS][VDL2_DUMPS_PER_ROW];	/* mixer dump schedules, one slot per distinct
+									   (fs, SDRCLK, format) in use; see Vdl2KParams.sched_slot */
 	unsigned char hcol[32];	/* header code parity-check columns, 25 used (viterbi.c:29-35) */
 };
 
@@ -80,9 +83,9 @@ struct Vdl2KParams {
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
 	const float4 *dcorr;	/* [nch][84]: per dump (1/nf, 1/nf, -cre/nf, -cim/nf), see dump_close */
-	const unsigned *sched;	/* [84]: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte chunks, then the
-				   chunk in which the dump ends after sample E; w0 = index of the dump's first chunk in the
-				   (extended) oscillator table.  Per handle: it depends on fs, SDRCLK and the sample format */
+	int sched_slot;		/* which c_tab.sched_slots[] row: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte
+				   chunks, then the chunk in which the dump ends after sample E; w0 = index of the dump's
+				   first chunk in the (extended) oscillator table */
 	unsigned *ticket;	/* work counter */
 	int *progress;		/* [nch]: tiles completed in this launch */
 	uint8_t *curblk;	/* [nch][2048] block under construction */

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "vdl2_kernel.h"
@@ -45,7 +46,7 @@ struct vdl2gpu {
 	Vdl2ChanState *d_state;
 	float4 *d_wtab;
 	float4 *d_dcorr;
-	unsigned *d_sched;
+	int sched_slot;
 	unsigned *d_ticket;
 	int *d_progress;
 	uint8_t *d_curblk;
@@ -217,6 +218,30 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	build_tables(*tab, sched_dump, h);
 	e = (cudaError_t) vdl2_kernel_upload_tables(tab);
 	delete tab;
+	if (e == cudaSuccess) {
+		/* the dump schedule depends on (fs, SDRCLK, format): handles with the same signature share a
+		   constant-memory slot (identical content), up to VDL2_SCHED_SLOTS signatures per device */
+		static std::mutex mtx;
+		static struct { unsigned fs, sdrclk; int fmt, dev; } slots[VDL2_SCHED_SLOTS];
+		static int nslots = 0;
+		std::lock_guard < std::mutex > lk(mtx);
+		h->sched_slot = -1;
+		for (int i = 0; i < nslots; i++)
+			if (slots[i].fs == cfg->fs && slots[i].sdrclk == cfg->sdrclk && slots[i].fmt == cfg->format && slots[i].dev == cfg->device)
+				h->sched_slot = i;
+		if (h->sched_slot < 0) {
+			if (nslots == VDL2_SCHED_SLOTS) {
+				delete h;
+				return fail(NULL, "vdl2_create: more than %d distinct (fs, sdrclk, format) combinations in one process", VDL2_SCHED_SLOTS);
+			}
+			slots[nslots].fs = cfg->fs;
+			slots[nslots].sdrclk = cfg->sdrclk;
+			slots[nslots].fmt = cfg->format;
+			slots[nslots].dev = cfg->device;
+			h->sched_slot = nslots++;
+		}
+		e = (cudaError_t) vdl2_kernel_upload_sched(h->sched_slot, sched_dump);
+	}
 	if (e != cudaSuccess) {
 		delete h;
 		return fail(NULL, "vdl2_create: constant table upload failed: %s", cudaGetErrorString(e));
@@ -310,8 +335,6 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
 	}
 
-	CK(h, cudaMalloc(&h->d_sched, sizeof sched_dump));
-	CK(h, cudaMemcpy(h->d_sched, sched_dump, sizeof sched_dump, cudaMemcpyHostToDevice));
 	CK(h, cudaMalloc(&h->d_ticket, 64));
 	CK(h, cudaMemset(h->d_ticket, 0, 64));
 	h->d_outq_count = h->d_ticket + 4;
@@ -370,7 +393,6 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
-	cudaFree(h->d_sched);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_curblk);
@@ -424,7 +446,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.state = h->d_state;
 	kp.wtab = h->d_wtab;
 	kp.dcorr = h->d_dcorr;
-	kp.sched = h->d_sched;
+	kp.sched_slot = h->sched_slot;
 	kp.ticket = h->d_ticket;
 	kp.progress = h->d_progress;
 	kp.curblk = h->d_curblk;

@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "vdl2_demod.cuh"
 #include "vdl2_kernel.h"
 
@@ -442,7 +443,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		} while (0)
 #pragma unroll 1
 		for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
-			const unsigned sk = __ldg(kp.sched + dk);
+			const unsigned sk = c_tab.sched_slots[kp.sched_slot][dk];
 			const int E = (int)((sk >> 8) & 255u);
 			const float4 *w = wsm + (sk >> 16);
 			int np = (int)(sk & 255u);
@@ -618,5 +619,15 @@ extern "C" int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm)
 
 extern "C" int vdl2_kernel_upload_tables(const Vdl2Tables * t)
 {
-	return (int)cudaMemcpyToSymbol(c_tab, t, sizeof(Vdl2Tables));
+	/* everything except the schedule slots (those are owned by vdl2_kernel_upload_sched) */
+	cudaError_t e = cudaMemcpyToSymbol(c_tab, t, offsetof(Vdl2Tables, sched_slots));
+	if (e != cudaSuccess)
+		return (int)e;
+	return (int)cudaMemcpyToSymbol(c_tab, t->hcol, sizeof t->hcol, offsetof(Vdl2Tables, hcol));
+}
+
+extern "C" int vdl2_kernel_upload_sched(int slot, const unsigned *sched)
+{
+	return (int)cudaMemcpyToSymbol(c_tab, sched, sizeof(unsigned) * VDL2_DUMPS_PER_ROW,
+				       offsetof(Vdl2Tables, sched_slots) + sizeof(unsigned) * VDL2_DUMPS_PER_ROW * slot);
 }
