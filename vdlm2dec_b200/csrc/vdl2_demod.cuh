@@ -54,6 +54,20 @@ VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
 VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
 VQ float fmul(float a, float b) { return __fmul_rn(a, b); }
 template <class T> VQ T ldcg(const T * p) { return __ldcg(p); }
+/* Blackwell packed fp32 (two independent IEEE operations per instruction) */
+VQ float2 fma2(float2 a, float2 b, float2 c)
+{
+	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a), rb = *reinterpret_cast < unsigned long long *>(&b);
+	unsigned long long rc = *reinterpret_cast < unsigned long long *>(&c), rd;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(rd):"l"(ra), "l"(rb), "l"(rc));
+	return *reinterpret_cast < float2 * >(&rd);
+}
+VQ float2 add2(float2 a, float2 b)
+{
+	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a), rb = *reinterpret_cast < unsigned long long *>(&b), rd;
+	asm("add.rn.f32x2 %0, %1, %2;":"=l"(rd):"l"(ra), "l"(rb));
+	return *reinterpret_cast < float2 * >(&rd);
+}
 }
 #else
 #include "vdl2_emul.h"		/* tests/emul: host definitions of VQ, VDL2_CONST and vw:: */
@@ -322,14 +336,12 @@ struct IdleScratch {
 /* filter only (no phase): 17 taps, steady-state tap phase */
 VQ void filt17(const float2 * sd, int d, const float *m, float &sr, float &si)
 {
-	sr = 0.f;
-	si = 0.f;
+	float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-	for (int j = 0; j < 17; j++) {
-		const float2 x = sd[d + j];
-		sr = vw::fma(x.x, m[j], sr);
-		si = vw::fma(x.y, m[j], si);
-	}
+	for (int j = 0; j < 17; j++)
+		s = vw::fma2(sd[d + j], make_float2(m[j], m[j]), s);	/* (re, im) * tap, same order as the scalar loop */
+	sr = s.x;
+	si = s.y;
 }
 
 /* three independent L2 loads per lane: window entries lane, lane+32, lane+64 starting at sd[g0] */
@@ -468,10 +480,11 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 			/* correlation with the unique word: q = 0,3,2,4,0,1,6,4,1,7,2,5,6,5,7,3 (multiples of pi/4) */
 			float2 A0 = make_float2(0.f, 0.f), A2 = A0, B0 = A0, B2 = A0;
 #define VDL2_ACC(L, Q) { const float2 w = S.vw[lane + 4 * (L)]; \
-	if ((Q) == 0) { A0.x += w.x; A0.y += w.y; } else if ((Q) == 4) { A0.x -= w.x; A0.y -= w.y; } \
-	else if ((Q) == 2) { A2.x += w.x; A2.y += w.y; } else if ((Q) == 6) { A2.x -= w.x; A2.y -= w.y; } \
-	else if ((Q) == 1) { B0.x += w.x; B0.y += w.y; } else if ((Q) == 5) { B0.x -= w.x; B0.y -= w.y; } \
-	else if ((Q) == 3) { B2.x += w.x; B2.y += w.y; } else { B2.x -= w.x; B2.y -= w.y; } }
+	if ((Q) == 0) A0 = vw::add2(A0, w); else if ((Q) == 4) A0 = vw::fma2(w, mone, A0); \
+	else if ((Q) == 2) A2 = vw::add2(A2, w); else if ((Q) == 6) A2 = vw::fma2(w, mone, A2); \
+	else if ((Q) == 1) B0 = vw::add2(B0, w); else if ((Q) == 5) B0 = vw::fma2(w, mone, B0); \
+	else if ((Q) == 3) B2 = vw::add2(B2, w); else B2 = vw::fma2(w, mone, B2); }
+			const float2 mone = make_float2(-1.f, -1.f);
 			VDL2_ACC(1, 0) VDL2_ACC(2, 3) VDL2_ACC(3, 2) VDL2_ACC(4, 4) VDL2_ACC(5, 0) VDL2_ACC(6, 1) VDL2_ACC(7, 6) VDL2_ACC(8, 4)
 			VDL2_ACC(9, 1) VDL2_ACC(10, 7) VDL2_ACC(11, 2) VDL2_ACC(12, 5) VDL2_ACC(13, 6) VDL2_ACC(14, 5) VDL2_ACC(15, 7) VDL2_ACC(16, 3)
 #undef VDL2_ACC
