@@ -51,6 +51,10 @@ enum vdl2_format {
    reference does (d8psk.c:259-289) instead of only where the screen says err < 4 is possible;
    same outputs, slower; implied by VDL2_TAP_STEPS */
 #define VDL2_OPT_EXACT_IDLE 0x100u
+/* option bit: mix cu8/cs8 input with the generic fp32 mixer (the one every other format uses) instead of
+   the integer dot-product mixer that is the default for 8-bit input at 2 Msps; same outputs within the
+   parity tolerance, slower; for A/B tests */
+#define VDL2_OPT_FLOAT_MIX 0x200u
 
 /* mirrors thread_param_t (vdlm2.h:49-52) */
 typedef struct {

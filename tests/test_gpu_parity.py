@@ -10,7 +10,7 @@ import pytest
 from oracle.pyoracle import Oracle
 from tests.parity_util import compare_channel, make_channels, run_oracle
 from vdlm2dec_b200 import synth
-from vdlm2dec_b200.api import OPT_EXACT_IDLE, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
+from vdlm2dec_b200.api import OPT_EXACT_IDLE, OPT_FLOAT_MIX, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
 
 pytestmark = pytest.mark.gpu
 ALL_TAPS = TAP_DUMPS | TAP_STEPS | TAP_SYNCS | TAP_SYMS  # TAP_STEPS implies the exact fit at every idle step
@@ -44,6 +44,26 @@ def test_parity_formats(fmt, screen):
     reps = _check_all(g, specs, iq, fmt, steps=not screen)
     assert sum(r["blocks"][0] for r in reps) >= nch  # the vectors do contain bursts
     assert g.stats()["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("fmt", ["cu8", "cs8"])
+def test_parity_float_mixer_for_8bit_input(fmt):
+    """8-bit input defaults to the integer dot-product mixer (exact int32 sums, weights quantised to 2^-22);
+    OPT_FLOAT_MIX selects the generic fp32 mixer all other formats use.  Both must meet the same parity bars,
+    and must agree with each other on every block."""
+    nch, n = 4, 900_000
+    specs, iq = make_channels(nch, n, seed=5, fmt=fmt)
+    chans = [(c, 136_975_000, specs[c].Fo) for c in range(nch)]
+    a = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS | OPT_FLOAT_MIX, max_samples=n)
+    a.process(iq)
+    ba = a.drain_blocks()
+    reps = _check_all(a, specs, iq, fmt, blocks=ba, steps=False)
+    assert sum(r["blocks"][0] for r in reps) >= nch
+    b = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS, max_samples=n)
+    b.process(iq)
+    bb = b.drain_blocks()
+    assert len(ba) == len(bb) and np.array_equal(ba["data"], bb["data"]) and np.array_equal(ba["sync_dump"], bb["sync_dump"])
+    _check_all(b, specs, iq, fmt, blocks=bb, steps=False)
 
 
 @pytest.mark.parametrize("fmt,fs,sdrclk,fos", [

@@ -17,6 +17,8 @@
 #define VDL2_PHHIST 64		/* idle-mode phases of history ((NBPH-1)*D8DWN) */
 #define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
 #define VDL2_SCHED_SLOTS 8	/* distinct (fs, SDRCLK, format) combinations alive in one process */
+#define VDL2_W8_PHASES 104	/* integer mixer: oscillator entries by NCO phase, 80 + 24 so that a dump never wraps */
+#define VDL2_W8_ENTRIES 120	/* ... plus 16 "first sample only" entries closing the 23-sample dumps of a row */
 #define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
 
 #define VDL2_FLAG_NO_SCREEN 1u	/* debug: run the exact 17-point fit at every idle step */
@@ -83,6 +85,8 @@ struct Vdl2KParams {
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
 	const float4 *dcorr;	/* [nch][84]: per dump (1/nf, 1/nf, -cre/nf, -cim/nf), see dump_close */
+	const uint4 *w8;	/* integer mixer only, [nch][VDL2_W8_ENTRIES]: (digit 2, digit 1, digit 0, 0) words of signed bytes
+				   (wr[n], wi[n], wr[n+1], wi[n+1]); sched word = (first sample << 16) | (last entry << 8) | first entry */
 	int sched_slot;		/* which c_tab.sched_slots[] row: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte
 				   chunks, then the chunk in which the dump ends after sample E; w0 = index of the dump's
 				   first chunk in the (extended) oscillator table */

@@ -46,6 +46,8 @@ struct vdl2gpu {
 	Vdl2ChanState *d_state;
 	float4 *d_wtab;
 	float4 *d_dcorr;
+	uint4 *d_w8;		/* integer mixer tables (dp4a mode only) */
+	int dp4a;		/* 1: cu8/cs8 at a rate whose dumps are 23/24 samples -> integer dot-product mixer */
 	int sched_slot;
 	unsigned *d_ticket;
 	int *d_progress;
@@ -132,6 +134,26 @@ static void build_tables(Vdl2Tables & t, unsigned *sched_dump, const vdl2gpu * h
 	/* dump schedule of one row (d8psk.c:374-381): dump k ends after sample e_k; it consists of np whole
 	   chunks plus the chunk holding e_k (np counts from the chunk after the previous boundary chunk) */
 	int clk = 0, k = 0, prev_c = -1;
+	if (h->dp4a) {
+		/* integer mixer: per dump (first sample << 16) | (table entry of its 12th sample pair << 8) | entry of its
+		   first pair.  Entries 0..103 are indexed by NCO phase; a 23-sample dump closes with one of the
+		   "first sample only" entries 104.. (assigned in row order, the same order the table builder uses) */
+		int start = 0, nshort = 0;
+		const int nco_n = h->cfg.fs / VDL2_STEPRATE;
+		for (int n = 0; n < h->row_samples; n++) {
+			clk += 21;
+			if (clk >= (int)h->cfg.sdrclk) {
+				clk %= (int)h->cfg.sdrclk;
+				const int len = n + 1 - start, w0 = start % nco_n;
+				const int wl = (len == 24) ? w0 + 22 : VDL2_W8_PHASES + nshort++;
+				if (k < VDL2_DUMPS_PER_ROW)
+					sched_dump[k] = ((unsigned)(getenv("VDL2_TEST_ALIGN") ? (start & ~7) : start) << 16) | ((unsigned)wl << 8) | (unsigned)w0;
+				start = n + 1;
+				k++;
+			}
+		}
+		return;
+	}
 	for (int n = 0; n < h->row_samples; n++) {
 		clk += 21;
 		if (clk >= (int)h->cfg.sdrclk) {
@@ -191,6 +213,25 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	const int nco_n = cfg->fs / VDL2_STEPRATE;	/* d8psk.c:348 */
 	h->nco_entries = (cfg->format == VDL2_FMT_CF32) ? nco_n : nco_n / 2;
 	h->n_sm = prop.multiProcessorCount;
+	/* integer mixer: 8-bit input whose dumps are all 23 or 24 samples long (2 Msps, SDRCLK 500: rtl.c:36-37) */
+	h->dp4a = 0;
+	h->d_w8 = NULL;
+	if ((cfg->format == VDL2_FMT_CU8 || cfg->format == VDL2_FMT_CS8) && !(cfg->taps & VDL2_OPT_FLOAT_MIX) && nco_n + 24 <= VDL2_W8_PHASES
+	    && getenv("VDL2_DP4A")) {	/* work in progress: opt-in until the window variants land */
+		int clk = 0, start = 0, ok = 1, nshort = 0;
+		for (int n = 0; n < h->row_samples; n++) {
+			clk += 21;
+			if (clk >= (int)cfg->sdrclk) {
+				clk %= (int)cfg->sdrclk;
+				const int len = n + 1 - start;
+				if (len != 23 && len != 24)
+					ok = 0;
+				nshort += (len == 23);
+				start = n + 1;
+			}
+		}
+		h->dp4a = ok && nshort <= VDL2_W8_ENTRIES - VDL2_W8_PHASES;
+	}
 
 	/* dump schedule sanity: exactly 84 dumps per row, clock back at 0, <= 1 boundary per chunk */
 	{
@@ -222,12 +263,13 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		/* the dump schedule depends on (fs, SDRCLK, format): handles with the same signature share a
 		   constant-memory slot (identical content), up to VDL2_SCHED_SLOTS signatures per device */
 		static std::mutex mtx;
-		static struct { unsigned fs, sdrclk; int fmt, dev; } slots[VDL2_SCHED_SLOTS];
+		static struct { unsigned fs, sdrclk; int fmt, dev, dp; } slots[VDL2_SCHED_SLOTS];
 		static int nslots = 0;
 		std::lock_guard < std::mutex > lk(mtx);
 		h->sched_slot = -1;
 		for (int i = 0; i < nslots; i++)
-			if (slots[i].fs == cfg->fs && slots[i].sdrclk == cfg->sdrclk && slots[i].fmt == cfg->format && slots[i].dev == cfg->device)
+			if (slots[i].fs == cfg->fs && slots[i].sdrclk == cfg->sdrclk && slots[i].fmt == cfg->format && slots[i].dev == cfg->device
+			    && slots[i].dp == h->dp4a)
 				h->sched_slot = i;
 		if (h->sched_slot < 0) {
 			if (nslots == VDL2_SCHED_SLOTS) {
@@ -238,6 +280,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 			slots[nslots].sdrclk = cfg->sdrclk;
 			slots[nslots].fmt = cfg->format;
 			slots[nslots].dev = cfg->device;
+			slots[nslots].dp = h->dp4a;
 			h->sched_slot = nslots++;
 		}
 		e = (cudaError_t) vdl2_kernel_upload_sched(h->sched_slot, sched_dump);
@@ -249,8 +292,8 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 
 	/* longest dump in chunks (+1 boundary chunk) times entries per chunk: how far past the table a dump can read */
 	h->wext = ((int)((cfg->fs / 84000 + 2 + h->spc - 1) / h->spc) + 1) * ((h->spc == 8) ? 4 : 2);
-	h->smem = vdl2_kernel_smem_bytes(h->nco_entries + h->wext);
-	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->smem, &h->ctas_per_sm);
+	h->smem = vdl2_kernel_smem_bytes(h->nco_entries + h->wext, h->dp4a);
+	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->dp4a, h->smem, &h->ctas_per_sm);
 	if (e != cudaSuccess || h->ctas_per_sm < 1) {
 		delete h;
 		return fail(NULL, "vdl2_create: kernel does not fit (smem %d B): %s", h->smem, cudaGetErrorString(e));
@@ -335,6 +378,79 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
 	}
 
+	if (h->dp4a) {
+		/* integer mixer tables.  W = round(w * 2^22) of the reference's float oscillator value, split into balanced
+		   base-256 digits W = d2*65536 + d1*256 + d0 (each in [-128,127], |d2| <= 64).  The kernel accumulates
+		     re_acc = sum Is*wr + (~Qs)*wi = sum Is*wr - Qs*wi - sum wi,    im_acc = sum Qs*wr + Is*wi
+		   with Is = I - 128 (cu8) or I (cs8), while the reference mixes x = Is + d, d = 128 - 127.37f (cu8) or 0, so
+		     re = re_acc + sum wi + d (sum wr - sum wi),   im = im_acc + d (sum wr + sum wi)
+		   (the "+ sum wi" uses the QUANTISED weights: it undoes an exact integer identity). */
+		std::vector < uint4 > w8((size_t) nch * VDL2_W8_ENTRIES);
+		std::vector < float4 > dc((size_t) nch * VDL2_DUMPS_PER_ROW);
+		const double d = (cfg->format == VDL2_FMT_CU8) ? 128.0 - (double)(float)127.37 : 0.0;
+		for (int c = 0; c < nch; c++) {
+			const float Fo = (float)((float)chans[c].Fo / (float)(cfg->fs) * 2.0 * M_PI);
+			std::vector < int >qr(nco_n), qi(nco_n);
+			std::vector < double >fr(nco_n), fi(nco_n);
+			for (int n = 0; n < nco_n; n++) {
+				const float a = (float)(-n) * Fo;
+				fr[n] = (double)cosf(a);
+				fi[n] = (double)sinf(a);
+				qr[n] = (int)lrint(fr[n] * 4194304.0);
+				qi[n] = (int)lrint(fi[n] * 4194304.0);
+			}
+			auto digits =[](int W, int dg[3]) {
+				dg[0] = ((W + 128) & 255) - 128;
+				W = (W - dg[0]) / 256;
+				dg[1] = ((W + 128) & 255) - 128;
+				dg[2] = (W - dg[1]) / 256;
+			};
+			auto entry =[&](int n, bool first_only) {
+				int a[3], b[3], a1[3] = { 0, 0, 0 }, b1[3] = { 0, 0, 0 };
+				digits(qr[n % nco_n], a);
+				digits(qi[n % nco_n], b);
+				if (!first_only) {
+					digits(qr[(n + 1) % nco_n], a1);
+					digits(qi[(n + 1) % nco_n], b1);
+				}
+				unsigned w[3];
+				for (int j = 0; j < 3; j++)
+					w[j] = (unsigned)(a[j] & 255) | ((unsigned)(b[j] & 255) << 8) | ((unsigned)(a1[j] & 255) << 16) | ((unsigned)(b1[j] & 255) << 24);
+				return make_uint4(w[2], w[1], w[0], 0u);
+			};
+			uint4 *wt = w8.data() + (size_t) c * VDL2_W8_ENTRIES;
+			for (int n = 0; n < VDL2_W8_PHASES; n++)
+				wt[n] = entry(n, false);
+			int clk = 0, start = 0, k = 0, nshort = 0;
+			long long sqi = 0;
+			double swr = 0, swi = 0;
+			for (int n = 0; n < h->row_samples; n++) {
+				sqi += qi[n % nco_n];
+				swr += fr[n % nco_n];
+				swi += fi[n % nco_n];
+				clk += 21;
+				if (clk >= (int)cfg->sdrclk) {
+					clk %= (int)cfg->sdrclk;
+					const int len = n + 1 - start;
+					if (len == 23)
+						wt[VDL2_W8_PHASES + nshort++] = entry(n, true);	/* the dump's last sample alone */
+					const double s = 1.0 / (double)len, q = 1.0 / 4194304.0;
+					const float sf = (float)(q * s);
+					if (k < VDL2_DUMPS_PER_ROW)
+						dc[(size_t) c * VDL2_DUMPS_PER_ROW + k] =
+						    make_float4(sf, sf, (float)(((double)sqi * q + d * (swr - swi)) * s), (float)((d * (swr + swi)) * s));
+					k++;
+					start = n + 1;
+					sqi = 0;
+					swr = swi = 0;
+				}
+			}
+		}
+		CK(h, cudaMalloc(&h->d_w8, sizeof(uint4) * w8.size()));
+		CK(h, cudaMemcpy(h->d_w8, w8.data(), sizeof(uint4) * w8.size(), cudaMemcpyHostToDevice));
+		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
+	}
+
 	CK(h, cudaMalloc(&h->d_ticket, 64));
 	CK(h, cudaMemset(h->d_ticket, 0, 64));
 	h->d_outq_count = h->d_ticket + 4;
@@ -393,6 +509,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
+	cudaFree(h->d_w8);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_curblk);
@@ -422,13 +539,24 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	if (((uintptr_t) base & 15) || (pitch & 15))
 		return fail(h, "input base/pitch must be 16-byte aligned for TMA (base %p pitch %zu)", base, pitch);
 	CUtensorMap tmap;
-	const cuuint64_t dims[3] = { (cuuint64_t) (h->row_bytes / 4), (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
 	const cuuint64_t strides[2] = { (cuuint64_t) h->row_bytes, (cuuint64_t) pitch };
-	const cuuint32_t box[3] = { 32, 32, 1 };
 	const cuuint32_t estr[3] = { 1, 1, 1 };
-	CUresult r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr,
-						     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-						     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r;
+	if (h->dp4a) {
+		/* one element = one IQ sample (2 bytes); a box = the 24 samples from the start of a dump, 32 rows; not
+		   swizzled (the 48-byte pitch is conflict free); samples past the end of a row read as zero */
+		const cuuint64_t dims[3] = { (cuuint64_t) h->row_samples, (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
+		const cuuint32_t box[3] = { 24, 32, 1 };
+		r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)base, dims, strides, box, estr,
+						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+						    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	} else {
+		const cuuint64_t dims[3] = { (cuuint64_t) (h->row_bytes / 4), (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
+		const cuuint32_t box[3] = { 32, 32, 1 };
+		r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr,
+						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+						    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	}
 	if (r != CUDA_SUCCESS)
 		return fail(h, "cuTensorMapEncodeTiled failed (%d): rows=%d row_bytes=%d pitch=%zu", (int)r, nrows, h->row_bytes, pitch);
 
@@ -446,6 +574,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.state = h->d_state;
 	kp.wtab = h->d_wtab;
 	kp.dcorr = h->d_dcorr;
+	kp.w8 = h->d_w8;
 	kp.sched_slot = h->sched_slot;
 	kp.ticket = h->d_ticket;
 	kp.progress = h->d_progress;
@@ -471,7 +600,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	const long long items = (long long)kp.ntiles * kp.nch;
 	const int grid = (int)std::min < long long >(items, h->grid);
 	CK(h, cudaEventRecord(h->ev0, h->stream));
-	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, &tmap, &kp, grid, h->smem, h->stream);
+	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, h->dp4a, &tmap, &kp, grid, h->smem, h->stream);
 	if (e != cudaSuccess)
 		return fail(h, "kernel launch failed: %s", cudaGetErrorString(e));
 	CK(h, cudaEventRecord(h->ev1, h->stream));

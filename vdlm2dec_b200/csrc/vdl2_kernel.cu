@@ -344,15 +344,121 @@ template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc &
 	}
 }
 
+/* ------------------------------------------------------------------ phase 1, 8-bit formats at 2 Msps: integer mixer
+ *
+ * Measured on B200 (tools/ubench): byte -> float conversion (2 PRMT + 1 FADD2 per sample) costs more
+ * pipe time than the complex MAC itself, and PRMT does not overlap FFMA2.  For cu8/cs8 input the mixer
+ * therefore runs on the integer dot-product unit, with no conversion at all:
+ *   - the oscillator value w[n] (the reference's float, d8psk.c:353-357) is quantised to 2^-22 and
+ *     split into three balanced base-256 digits; one table word per digit holds the four signed bytes
+ *     (wr[n], wi[n], wr[n+1], wi[n+1]);
+ *   - a data word (I0 Q0 I1 Q1) is made signed with one XOR; a second XOR pattern turns Q into ~Q = -Q-1
+ *     so that ONE weight word serves both components:
+ *         re += dp4a((I, ~Q), (wr, wi))      im += dp4a((Q, I), (wr, wi))          (IDP.4A, 3 digits each)
+ *     the -sum(wi) left by ~Q and the 127.37f / 128 offset of rtl.c:287-289 are linear in w and are
+ *     applied per dump from the dcorr table (built in double on the host);
+ *   - the six int32 sums are exact; they are combined in fp32 at the dump close (relative error 1e-7,
+ *     the weight quantisation contributes < 1e-7 of the dump rms: tests/test_gpu_parity.py).
+ * Dump boundaries never fall inside a word because the TMA boxes are DUMP ALIGNED: the tensor map has
+ * 2-byte elements (one IQ sample), box k = 24 samples x 32 rows starting at the first sample of dump k
+ * (no swizzle: the 48-byte row pitch is already conflict free for LDS.128).  A 23-sample dump reads one
+ * sample too many; its last table entry has zero weights for it.
+ * Dumps are transposed through a small shared tile so that the scratch stores are coalesced (one
+ * STG.64 per dump used to touch 32 sectors).
+ */
+#define D8_NST VDL2_D8_NST
+#define D8_STAGE 1536
+#define D8_TPITCH 9		/* float2 per row of the transpose tile: 8 dumps + 1 pad (conflict-free STS.64) */
+
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c)
+{
+	return __dp4a((int)a, (int)b, c);
+}
+
+template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtensorMap * tmap, const Vdl2KParams & kp, unsigned char *stage0,
+								 unsigned long long *bars, float2 * tile, const uint4 * w8, uint32_t & phases,
+								 int row0, int stream, const float4 * dcorr, float2 * sd,
+								 unsigned long long l2pol)
+{
+	const int lane = threadIdx.x;
+	const unsigned *sched = c_tab.sched_slots[kp.sched_slot];
+	const uint32_t KR = (FMT == VDL2_FMT_CU8) ? 0x7F807F80u : 0xFF00FF00u;	/* I -> signed, Q -> ~signed */
+	const uint32_t KS = (FMT == VDL2_FMT_CU8) ? 0x80808080u : 0u;
+	const unsigned char *rowp = stage0 + lane * 48;
+	int st = 0;		/* stage of the dump whose data are being loaded */
+	mbar_wait(smem_u32(bars), phases & 1u);
+	phases ^= 1u;
+	uint4 n0 = *reinterpret_cast < const uint4 * >(rowp);
+	uint4 n1 = *reinterpret_cast < const uint4 * >(rowp + 16);
+	uint4 n2 = *reinterpret_cast < const uint4 * >(rowp + 32);
+	float4 dcn = __ldg(dcorr);
+#pragma unroll 2
+	for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
+		const uint32_t d[12] = { n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w };
+		const float4 dc = dcn;
+		const unsigned sk = sched[dk];
+		const int cur = st;
+		if (dk + 1 < VDL2_DUMPS_PER_ROW) {	/* data of the next dump: in registers before this one is mixed */
+			st = (st + 1 == D8_NST) ? 0 : st + 1;
+			mbar_wait(smem_u32(bars + st), (phases >> st) & 1u);
+			phases ^= 1u << st;
+			const unsigned char *p = rowp + st * D8_STAGE;
+			n0 = *reinterpret_cast < const uint4 * >(p);
+			n1 = *reinterpret_cast < const uint4 * >(p + 16);
+			n2 = *reinterpret_cast < const uint4 * >(p + 32);
+			dcn = __ldg(dcorr + dk + 1);
+		}
+		const uint4 *wt = w8 + (sk & 255u);
+		int re2 = 0, re1 = 0, re0 = 0, im2 = 0, im1 = 0, im0 = 0;
+#pragma unroll
+		for (int p = 0; p < 12; p++) {
+			const uint4 W = (p == 11) ? w8[(sk >> 8) & 255u] : wt[2 * p];
+			const uint32_t xr = d[p] ^ KR;
+			const uint32_t xs = __byte_perm(d[p], 0u, 0x2301) ^ KS;
+			re2 = dp4a_ss(xr, W.x, re2);
+			im2 = dp4a_ss(xs, W.x, im2);
+			re1 = dp4a_ss(xr, W.y, re1);
+			im1 = dp4a_ss(xs, W.y, im1);
+			re0 = dp4a_ss(xr, W.z, re0);
+			im0 = dp4a_ss(xs, W.z, im0);
+		}
+		const float fr = fmaf((float)re2, 65536.f, fmaf((float)re1, 256.f, (float)re0));
+		const float fi = fmaf((float)im2, 65536.f, fmaf((float)im1, 256.f, (float)im0));
+		tile[lane * D8_TPITCH + (dk & 7)] = ffma2(make_float2(fr, fi), make_float2(dc.x, dc.y), make_float2(dc.z, dc.w));
+		__syncwarp();	/* every lane has consumed the stage dump dk came from */
+		if (lane == 0 && dk + D8_NST < VDL2_DUMPS_PER_ROW) {
+			const uint32_t bar = smem_u32(bars + cur);
+			mbar_expect_tx(bar, D8_STAGE);
+			tma_load_3d(smem_u32(stage0 + cur * D8_STAGE), tmap, bar, (int)(sched[dk + D8_NST] >> 16), row0, stream, l2pol);
+		}
+		if ((dk & 7) == 7 || dk == VDL2_DUMPS_PER_ROW - 1) {
+			/* 8 (last group: 4) dumps x 32 rows -> scratch, 64 contiguous bytes per row */
+			const int k0 = dk & ~7, ng = dk - k0 + 1;
+			const int col = lane & 7, rsub = lane >> 3;
+			float2 *dst = sd + VDL2_HIST + k0 + col;
+#pragma unroll
+			for (int it = 0; it < 8; it++) {
+				const int r = it * 4 + rsub;
+				if (col < ng)
+					__stcg(dst + r * VDL2_DUMPS_PER_ROW, tile[r * D8_TPITCH + col]);
+			}
+			__syncwarp();
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ the kernel */
-template < int FMT > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
+template < int FMT, bool DP > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
 vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const int lane = threadIdx.x;
 	unsigned char *stage0 = smem;
-	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + NSTAGE * STAGE_BYTES);
-	float *hv = reinterpret_cast < float *>(smem + NSTAGE * STAGE_BYTES + 64);
+	/* stages (+ the transpose tile of the integer mixer) | mbarriers | header soft bits | oscillator table */
+	constexpr int STAGES_BYTES = DP ? D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 : NSTAGE * STAGE_BYTES;
+	constexpr int NBAR = DP ? D8_NST : NSTAGE;
+	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + STAGES_BYTES);
+	float *hv = reinterpret_cast < float *>(smem + STAGES_BYTES + 64);
 	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
 	/* the decimated stream of the tile lives in global memory (L2): sd[0..15] history, sd[16 + i] dump i */
 	float2 *sd = kp.scratch + (size_t) blockIdx.x * (VDL2_HIST + VDL2_TILE_DUMPS);
@@ -362,13 +468,14 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	scr.vw = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4);
 	scr.win = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
 	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8);
-	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + VDL2_CAND_CAP * 2 <= NSTAGE * STAGE_BYTES,
+	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + VDL2_CAND_CAP * 2 <= STAGES_BYTES,
 		      "phase 2 scratch must fit the stages");
+	static_assert(NBAR <= 8, "mbarriers live in 64 bytes");
 
 	if ((smem_u32(smem) & 1023u) != 0)
 		__trap();	/* the 128B swizzle pattern assumes 1 KiB aligned stages */
 	if (lane == 0) {
-		for (int s = 0; s < NSTAGE; s++)
+		for (int s = 0; s < NBAR; s++)
 			mbar_init(smem_u32(bars + s), 1);
 		asm volatile ("fence.mbarrier_init.release.cluster;":::"memory");
 	}
@@ -398,81 +505,99 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		const int nrows = min(VDL2_ROWS_PER_TILE, kp.nrows - row0);
 		const int nd = nrows * VDL2_DUMPS_PER_ROW;
 
-		/* prologue: first boxes in flight, oscillator table to shared memory */
-		if (lane == 0) {
-			for (int b = 0; b < NSTAGE && b < nbox; b++) {
-				const uint32_t bar = smem_u32(bars + b);
-				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream, l2pol);
-			}
-		}
-		for (int i = lane; i < nco + kp.wext; i += 32)
-			wsm[i] = kp.wtab[(size_t) ch * nco + (i < nco ? i : i - nco)];
-		__syncwarp();
-
-		/* ---- phase 1: dump-centric walk over the row.  Dump k = np plain chunks + the chunk it ends in
-		   (after sample E); chunks come from the TMA ring, 8 per 128-byte box; the oscillator table is
-		   addressed from a per-dump base (no wrap inside a dump: the table is extended). ---- */
-		MixAcc acc;
-		acc_zero(acc);
 		const float4 *dcorr = kp.dcorr + (size_t) ch * VDL2_DUMPS_PER_ROW;
-		int k = 0, bx = 0, j = 0;
-		mbar_wait(smem_u32(bars), phases & 1u);
-		phases ^= 1u;
-		const unsigned char *rowp = stage0 + lane * 128;
-#define VDL2_LOAD_CHUNK() (*reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4)))
-#define VDL2_NEXT_CHUNK()                                                                                  \
-		do {                                                                                        \
-			if (++j == 8) {                                                                     \
-				j = 0;                                                                      \
-				__syncwarp();                                                               \
-				const int slot_ = bx % NSTAGE;                                              \
-				if (lane == 0 && bx + NSTAGE < nbox) {                                      \
-					const uint32_t bar_ = smem_u32(bars + slot_);                       \
-					mbar_expect_tx(bar_, STAGE_BYTES);                                  \
-					tma_load_3d(smem_u32(stage0 + slot_ * STAGE_BYTES), &tmap, bar_, (bx + NSTAGE) * 32, row0, stream, l2pol); \
-				}                                                                           \
-				bx++;                                                                       \
-				if (bx < nbox) {                                                            \
-					const int ns_ = bx % NSTAGE;                                        \
-					mbar_wait(smem_u32(bars + ns_), (phases >> ns_) & 1u);              \
-					phases ^= 1u << ns_;                                                \
-					rowp = stage0 + ns_ * STAGE_BYTES + lane * 128;                     \
-				}                                                                           \
-			}                                                                                   \
-		} while (0)
-#pragma unroll 1
-		for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
-			const unsigned sk = c_tab.sched_slots[kp.sched_slot][dk];
-			const int E = (int)((sk >> 8) & 255u);
-			const float4 *w = wsm + (sk >> 16);
-			int np = (int)(sk & 255u);
-#ifdef VDL2_UNROLL_NP2
-			if (np == 2) {	/* the common shape at 2 Msps: 24 (23) samples = 2 whole chunks + the boundary chunk */
-				uint4 v = VDL2_LOAD_CHUNK();
-				chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
-				VDL2_NEXT_CHUNK();
-				v = VDL2_LOAD_CHUNK();
-				chunk_plain < FMT > (acc, v, w + wpc, sdrow, dcorr, k);
-				VDL2_NEXT_CHUNK();
-				w += 2 * wpc;
-			} else
-#endif
-			{
-#pragma unroll 1
-				for (; np > 0; np--) {
-					const uint4 v = VDL2_LOAD_CHUNK();
-					chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
-					VDL2_NEXT_CHUNK();
-					w += wpc;
+		if (DP) {
+			/* ---- phase 1, integer mixer: dump-aligned boxes, see mix_rows_dp4a ---- */
+			if (lane == 0) {
+				for (int b = 0; b < D8_NST; b++) {
+					const uint32_t bar = smem_u32(bars + b);
+					mbar_expect_tx(bar, D8_STAGE);
+					tma_load_3d(smem_u32(stage0 + b * D8_STAGE), &tmap, bar, (int)(c_tab.sched_slots[kp.sched_slot][b] >> 16), row0,
+						    stream, l2pol);
 				}
 			}
-			const uint4 v = VDL2_LOAD_CHUNK();
-			chunk_bound < FMT > (E, acc, v, w, sdrow, dcorr, k);
-			VDL2_NEXT_CHUNK();
+			uint4 *w8 = reinterpret_cast < uint4 * >(wsm);
+			for (int i = lane; i < VDL2_W8_ENTRIES; i += 32)
+				w8[i] = __ldg(kp.w8 + (size_t) ch * VDL2_W8_ENTRIES + i);
+			__syncwarp();
+			mix_rows_dp4a < FMT > (&tmap, kp, stage0, bars, reinterpret_cast < float2 * >(smem + D8_NST * D8_STAGE), w8, phases, row0,
+					       stream, dcorr, sd, l2pol);
+		} else {
+			/* prologue: first boxes in flight, oscillator table to shared memory */
+			if (lane == 0) {
+				for (int b = 0; b < NSTAGE && b < nbox; b++) {
+					const uint32_t bar = smem_u32(bars + b);
+					mbar_expect_tx(bar, STAGE_BYTES);
+					tma_load_3d(smem_u32(stage0 + b * STAGE_BYTES), &tmap, bar, b * 32, row0, stream, l2pol);
+				}
+			}
+			for (int i = lane; i < nco + kp.wext; i += 32)
+				wsm[i] = kp.wtab[(size_t) ch * nco + (i < nco ? i : i - nco)];
+			__syncwarp();
+
+			/* ---- phase 1: dump-centric walk over the row.  Dump k = np plain chunks + the chunk it ends in
+			   (after sample E); chunks come from the TMA ring, 8 per 128-byte box; the oscillator table is
+			   addressed from a per-dump base (no wrap inside a dump: the table is extended). ---- */
+			MixAcc acc;
+			acc_zero(acc);
+			int k = 0, bx = 0, j = 0;
+			mbar_wait(smem_u32(bars), phases & 1u);
+			phases ^= 1u;
+			const unsigned char *rowp = stage0 + lane * 128;
+	#define VDL2_LOAD_CHUNK() (*reinterpret_cast < const uint4 * >(rowp + ((j ^ l7) << 4)))
+	#define VDL2_NEXT_CHUNK()                                                                                  \
+			do {                                                                                        \
+				if (++j == 8) {                                                                     \
+					j = 0;                                                                      \
+					__syncwarp();                                                               \
+					const int slot_ = bx % NSTAGE;                                              \
+					if (lane == 0 && bx + NSTAGE < nbox) {                                      \
+						const uint32_t bar_ = smem_u32(bars + slot_);                       \
+						mbar_expect_tx(bar_, STAGE_BYTES);                                  \
+						tma_load_3d(smem_u32(stage0 + slot_ * STAGE_BYTES), &tmap, bar_, (bx + NSTAGE) * 32, row0, stream, l2pol); \
+					}                                                                           \
+					bx++;                                                                       \
+					if (bx < nbox) {                                                            \
+						const int ns_ = bx % NSTAGE;                                        \
+						mbar_wait(smem_u32(bars + ns_), (phases >> ns_) & 1u);              \
+						phases ^= 1u << ns_;                                                \
+						rowp = stage0 + ns_ * STAGE_BYTES + lane * 128;                     \
+					}                                                                           \
+				}                                                                                   \
+			} while (0)
+	#pragma unroll 1
+			for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
+				const unsigned sk = c_tab.sched_slots[kp.sched_slot][dk];
+				const int E = (int)((sk >> 8) & 255u);
+				const float4 *w = wsm + (sk >> 16);
+				int np = (int)(sk & 255u);
+	#ifdef VDL2_UNROLL_NP2
+				if (np == 2) {	/* the common shape at 2 Msps: 24 (23) samples = 2 whole chunks + the boundary chunk */
+					uint4 v = VDL2_LOAD_CHUNK();
+					chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
+					VDL2_NEXT_CHUNK();
+					v = VDL2_LOAD_CHUNK();
+					chunk_plain < FMT > (acc, v, w + wpc, sdrow, dcorr, k);
+					VDL2_NEXT_CHUNK();
+					w += 2 * wpc;
+				} else
+	#endif
+				{
+	#pragma unroll 1
+					for (; np > 0; np--) {
+						const uint4 v = VDL2_LOAD_CHUNK();
+						chunk_plain < FMT > (acc, v, w, sdrow, dcorr, k);
+						VDL2_NEXT_CHUNK();
+						w += wpc;
+					}
+				}
+				const uint4 v = VDL2_LOAD_CHUNK();
+				chunk_bound < FMT > (E, acc, v, w, sdrow, dcorr, k);
+				VDL2_NEXT_CHUNK();
+			}
+	#undef VDL2_NEXT_CHUNK
+	#undef VDL2_LOAD_CHUNK
 		}
-#undef VDL2_NEXT_CHUNK
-#undef VDL2_LOAD_CHUNK
 		__threadfence_block();
 		__syncwarp();
 
@@ -571,48 +696,64 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 }				/* namespace vdl2 */
 
 /* ------------------------------------------------------------------ launch shims used by vdl2_host.cu */
-extern "C" int vdl2_kernel_smem_bytes(int nco_entries)
+extern "C" int vdl2_kernel_smem_bytes(int nco_entries, int dp4a)
 {
+	if (dp4a)
+		return D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 + 64 + 32 * 4 + VDL2_W8_ENTRIES * 16;
 	return VDL2_NSTAGE * STAGE_BYTES + 64 + 32 * 4 + nco_entries * 16;
 }
 
-template < int FMT > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+template < int FMT, bool DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess)
 		return e;
-	vdl2::vdl2_frontend_kernel < FMT > <<<grid, 32, smem, st >>> (tmap, kp);
+	vdl2::vdl2_frontend_kernel < FMT, DP > <<<grid, 32, smem, st >>> (tmap, kp);
 	return cudaGetLastError();
 }
 
-extern "C" int vdl2_kernel_launch(int fmt, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream)
+extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream)
 {
 	const CUtensorMap & m = *reinterpret_cast < const CUtensorMap * >(tmap);
 	cudaStream_t st = (cudaStream_t) stream;
+	if (dp4a) {
+		switch (fmt) {
+		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, true > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, true > (m, *kp, grid, smem, st);
+		}
+		return (int)cudaErrorInvalidValue;
+	}
 	switch (fmt) {
-	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, false > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, false > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32, false > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16, false > (m, *kp, grid, smem, st);
+	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL, false > (m, *kp, grid, smem, st);
 	}
 	return (int)cudaErrorInvalidValue;
 }
 
-template < int FMT > static cudaError_t occ_fmt(int smem, int *n)
+template < int FMT, bool DP > static cudaError_t occ_fmt(int smem, int *n)
 {
-	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, vdl2::vdl2_frontend_kernel < FMT >, 32, smem);
+	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, vdl2::vdl2_frontend_kernel < FMT, DP >, 32, smem);
 }
 
-extern "C" int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm)
+extern "C" int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm)
 {
+	if (dp4a) {
+		switch (fmt) {
+		case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, true > (smem, ctas_per_sm);
+		case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, true > (smem, ctas_per_sm);
+		}
+		return (int)cudaErrorInvalidValue;
+	}
 	switch (fmt) {
-	case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8 > (smem, ctas_per_sm);
-	case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8 > (smem, ctas_per_sm);
-	case VDL2_FMT_CF32: return (int)occ_fmt < VDL2_FMT_CF32 > (smem, ctas_per_sm);
-	case VDL2_FMT_CS16: return (int)occ_fmt < VDL2_FMT_CS16 > (smem, ctas_per_sm);
-	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL > (smem, ctas_per_sm);
+	case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, false > (smem, ctas_per_sm);
+	case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, false > (smem, ctas_per_sm);
+	case VDL2_FMT_CF32: return (int)occ_fmt < VDL2_FMT_CF32, false > (smem, ctas_per_sm);
+	case VDL2_FMT_CS16: return (int)occ_fmt < VDL2_FMT_CS16, false > (smem, ctas_per_sm);
+	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL, false > (smem, ctas_per_sm);
 	}
 	return (int)cudaErrorInvalidValue;
 }

@@ -11,12 +11,16 @@
 #define VDL2_MIN_CTAS 16
 #endif		/* TMA boxes (32 rows x 128 B) in flight per warp */
 
+#ifndef VDL2_D8_NST
+#define VDL2_D8_NST 6		/* dump-aligned TMA boxes (32 rows x 48 B) in flight per warp, integer mixer */
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
-int vdl2_kernel_smem_bytes(int nco_entries);
-int vdl2_kernel_launch(int fmt, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream);
-int vdl2_kernel_occupancy(int fmt, int smem, int *ctas_per_sm);
+int vdl2_kernel_smem_bytes(int nco_entries, int dp4a);
+int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream);
+int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm);
 int vdl2_kernel_upload_tables(const struct Vdl2Tables *t);
 int vdl2_kernel_upload_sched(int slot, const unsigned *sched);
 #ifdef __cplusplus
