@@ -37,6 +37,9 @@ struct TileJob {
 	vdl2::IdleScratch S;
 	float *hv;
 	int nph[32];
+	int pre_mode;		/* 0: no speculative pass A; 1: with the right clock guess; 2: with a wrong / stale guess */
+	float2 hist[VDL2_HIST];	/* the real history, made visible only after the prepass (as in the kernel) */
+	float ph_hist[VDL2_PHHIST];
 	vdl2::ChanRegs R0;
 	vdl2::ChanRegs Rout[32];
 };
@@ -47,7 +50,30 @@ static void lane_main(int lane)
 	TileJob *j = g_job;
 	vdl2::ChanRegs R = j->R0;
 	int nph = 0;
-	vdl2::demod_tile(*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->S, j->hv, j->nd, j->dump_base, nph);
+	vdl2::IdlePre pre;
+	pre.valid = 0;
+	pre.used = 0;
+	if (j->pre_mode) {
+		/* the kernel runs the speculative stage BEFORE it has the previous tile's state: only a guess of (state, clk) */
+		const int cg = j->pre_mode == 1 ? R.clk : ((R.clk + 3) & 7);
+		const int sg = j->pre_mode == 1 ? R.state : VDL2_ST_WSYNC;
+		if (sg == VDL2_ST_WSYNC && cg >= 0 && cg < 8) {
+			vdl2::ChanRegs G;
+			memset(&G, 0, sizeof G);
+			G.clk = cg;
+			G.state = VDL2_ST_WSYNC;
+			G.perr = 100.f;
+			int nph0 = 0;
+			vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, G, j->sd, j->S, j->hv, j->nd, j->dump_base, nph0, pre, true);
+		}
+		vw::sync();
+		if (lane < VDL2_HIST)
+			j->sd[lane] = j->hist[lane];
+		j->S.pht[lane] = j->ph_hist[lane];
+		j->S.pht[lane + 32] = j->ph_hist[lane + 32];
+		vw::sync();
+	}
+	vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->S, j->hv, j->nd, j->dump_base, nph, pre, false);
 	j->nph[lane] = nph;
 	j->Rout[lane] = R;
 	vw::g_done[lane] = 1;
@@ -133,7 +159,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	kp.outq_cap = cap_blocks;
 	kp.dropped = &dropped;
 	kp.taps = (steps ? VDL2_TAP_STEPS_BIT : 0u) | VDL2_TAP_SYNCS_BIT | VDL2_TAP_SYMS_BIT;
-	kp.flags = flags;
+	kp.flags = flags & 0xffu;
 	kp.tap_steps = steps;
 	kp.tap_syncs = syncs;
 	kp.tap_syms = syms;
@@ -145,7 +171,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	float hv[32] = { 0 };
 	std::vector < float >pht(VDL2_PHT_LEN, 0.f);
 	std::vector < float2 > vwin(96);
-	std::vector < unsigned short >cand(VDL2_CAND_CAP);
+	std::vector < unsigned short >cand(VDL2_CAND_CAP + VDL2_CAND0_CAP);
 	std::vector < float2 > win(VDL2_WIN_LEN);
 	for (int i = 0; i < VDL2_HIST; i++)
 		sd[i] = make_float2(0.f, 0.f);
@@ -169,6 +195,18 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 		job.S.pht = pht.data();
 		job.S.vw = vwin.data();
 		job.S.cand = cand.data();
+		job.S.cand0 = cand.data() + VDL2_CAND_CAP;
+		job.pre_mode = (flags & 0x100u) ? 1 : ((flags & 0x200u) ? 2 : 0);
+		if (job.pre_mode) {
+			for (int i = 0; i < VDL2_HIST; i++) {
+				job.hist[i] = sd[i];
+				sd[i] = make_float2(37.f * (float)(i + 1), -11.f * (float)i);	/* stale scratch content */
+			}
+			for (int i = 0; i < VDL2_PHHIST; i++) {
+				job.ph_hist[i] = pht[i];
+				pht[i] = 0.1f * (float)i;
+			}
+		}
 		job.S.win = win.data();
 		job.hv = hv;
 		job.R0 = R;

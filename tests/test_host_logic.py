@@ -57,6 +57,24 @@ def test_phase2_source_matches_oracle(tile):
     assert rep["gi_flips"] <= 2
 
 
+@pytest.mark.parametrize("tile", [2688, 84 * 12])
+@pytest.mark.parametrize("mode", [0x100, 0x200])
+def test_phase2_speculative_pass_a(tile, mode):
+    """The kernel screens the idle steps of a tile BEFORE it has the previous tile's state, from a guess of the
+    tick clock (idle_prepass); idle_run verifies the guess.  With the right guess (0x100) and with a wrong one /
+    a stale 'idle' guess during a burst (0x200) the events must equal the plain screened search and the oracle."""
+    n = 1_500_000
+    spec = synth.standard_channel(seed=33, nsamples=n, Fo=-125_000, period=45_000, payload_bytes=(14, 500))
+    iq = synth.render_channel(spec, n)
+    o = Oracle("port", Fo=-125_000).feed(iq)
+    assert len(o.blocks) >= 4
+    b0, _, sy0, sm0 = emul.demod(o.dumps, tile, want_steps=False)
+    b1, _, sy1, sm1 = emul.demod(o.dumps, tile, flags=mode, want_steps=False)
+    assert len(b0) == len(b1) and np.array_equal(b0["data"], b1["data"]) and np.array_equal(b0["sync_dump"], b1["sync_dump"])
+    assert sy0.tobytes() == sy1.tobytes() and sm0.tobytes() == sm1.tobytes()
+    compare_channel(o, b1, sy1, sm1, None, None)
+
+
 @pytest.mark.parametrize("nlbyte_class", ["le2", "le30", "le67", "gt67", "zero", "rows8"])
 def test_phase2_edge_lengths(nlbyte_class):
     length = {"le2": 1992 + 12, "le30": 1992 + 8 * 20, "le67": 1992 + 8 * 50, "gt67": 1992 + 8 * 100, "zero": 1992,

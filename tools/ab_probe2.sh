@@ -1,0 +1,7 @@
+#!/bin/bash
+# same-box A/B over library variants: noise probe (idle-mode worst case) and burst probe (bench-like)
+for lib in "$@"; do
+  n=$(VDL2_LIB=$PWD/vdlm2dec_b200/$lib python tools/perf_probe.py 1024 2097152 4 2>&1 | grep "^rep 3" | awk '{print $3}')
+  b=$(VDL2_LIB=$PWD/vdlm2dec_b200/$lib python tools/perf_probe.py 1024 4194000 4 1 bursts 2>&1 | grep "^rep 3" | awk '{print $3}')
+  echo "$lib noise_ms=$n bursts_ms=$b"
+done

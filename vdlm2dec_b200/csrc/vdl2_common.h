@@ -16,12 +16,13 @@
 #define VDL2_HIST 16		/* dumps of history in front of a tile (MBUFLEN-1) */
 #define VDL2_PHHIST 64		/* idle-mode phases of history ((NBPH-1)*D8DWN) */
 #define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
-#define VDL2_SCHED_SLOTS 8	/* distinct (fs, SDRCLK, format) combinations alive in one process */
+#define VDL2_SCHED_SLOTS 16	/* distinct (fs, SDRCLK, format) combinations alive in one process */
 #define VDL2_W8_PHASES 104	/* integer mixer: oscillator entries by NCO phase, 80 + 24 so that a dump never wraps */
 #define VDL2_W8_ENTRIES 120	/* ... plus 16 "first sample only" entries closing the 23-sample dumps of a row */
 #define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
 
 #define VDL2_FLAG_NO_SCREEN 1u	/* debug: run the exact 17-point fit at every idle step */
+#define VDL2_FLAG_NO_PREPASS 2u	/* A/B: no speculative pass A while waiting for the previous tile */
 #define VDL2_TAP_DUMPS_BIT 1u
 #define VDL2_TAP_STEPS_BIT 2u
 #define VDL2_TAP_SYNCS_BIT 4u
@@ -44,7 +45,12 @@ struct Vdl2ChanState {
 	int64_t sync_dump;
 	int32_t chn, Fr;
 	uint32_t n_steps, n_syncs, n_syms, n_dumps;	/* tap record counts */
-	int32_t pad[6];
+	/* forecast for the speculative idle search of later tiles: as far as is known the channel is idle from global dump
+	   fc_dump on, with tick clock fc_clk there.  Written at the end of an idle tile and, early, as soon as the header
+	   of a burst gives its length; read without synchronisation (a wrong guess is detected, see idle_run) */
+	int64_t fc_dump;
+	int32_t fc_clk;
+	int32_t pad[3];
 };
 
 /* constant tables of the kernel (independent of rate and format, so handles can share them) */

@@ -34,6 +34,16 @@
 #ifdef __CUDACC__
 #define VQ __device__ __forceinline__
 #define VQ_COLD __device__ __noinline__	/* rare paths: kept out of line so the hot loops stay I-cache resident */
+#ifdef VDL2_OUTLINE_RARE	/* A/B: measured slower on the burst workload (state forced through local memory around the calls) */
+#define VQ_RARE __device__ __noinline__
+#else
+#define VQ_RARE __device__ __forceinline__
+#endif
+#ifdef VDL2_PASSA_OUTLINE	/* A/B: 8 % slower on the whole kernel */
+#define VQ_PASSA __device__ __noinline__
+#else
+#define VQ_PASSA __device__ __forceinline__
+#endif
 #define VDL2_CONST __constant__
 namespace vw {
 VQ int lane() { return threadIdx.x & 31; }
@@ -46,14 +56,31 @@ VQ void fence() { __threadfence(); }
 VQ int ffs(unsigned m) { return __ffs(m); }
 VQ int popc(unsigned m) { return __popc(m); }
 VQ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+#ifdef VDL2_ATAN2_NOINLINE
+__device__ __noinline__ float atan2(float y, float x) { return atan2f(y, x); }
+#else
 VQ float atan2(float y, float x) { return atan2f(y, x); }
+#endif
+#ifdef VDL2_SLOW_SINCOS
 VQ void sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
+#else
+/* only the correlation screen uses this (phases in [-pi, pi], 1e-6 is plenty): SFU sine / cosine */
+VQ void sincos(float a, float &s, float &c) { s = __sinf(a); c = __cosf(a); }
+#endif
 VQ float rsqrt(float a) { return rsqrtf(a); }
 VQ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
 VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
 VQ float fmul(float a, float b) { return __fmul_rn(a, b); }
 template <class T> VQ T ldcg(const T * p) { return __ldcg(p); }
+/* A pointer that went through the argument list of an out-of-line function is a generic pointer: every access
+   becomes a generic LD/ST.  Re-derive it from the dynamic shared array so that the compiler knows the address
+   space again (LDS / STS, vector widths) -- measured 8 % of the whole kernel on idle_passA. */
+template <class T> VQ T *as_shared(T * p)
+{
+	extern __shared__ __align__(1024) unsigned char vdl2_smem_base[];
+	return reinterpret_cast < T * >(vdl2_smem_base + (__cvta_generic_to_shared(p) - __cvta_generic_to_shared(vdl2_smem_base)));
+}
 /* Blackwell packed fp32 (two independent IEEE operations per instruction) */
 VQ float2 fma2(float2 a, float2 b, float2 c)
 {
@@ -134,8 +161,9 @@ VQ float filt_phase_any(const float2 * sd, int d, int clk)
 
 /* 17-point least-squares line through the unwrapped (phase - unique word) sequence
    (d8psk.c:259-289).  ph[4*l] is the phase of symbol l.  Returns residual and slope. */
-VQ_COLD float2 sync_fit_nv(const float *ph)
+VQ_COLD float2 sync_fit_nv(const float *ph_generic)
 {
+	const float *ph = vw::as_shared(ph_generic);
 	float Pr[VDL2_NBPH];
 	float kf = 0.f, Pv, M;
 	M = Pv = Pr[0] = ph[0] - c_tab.sync[0];
@@ -242,7 +270,8 @@ VQ_COLD unsigned header_decode(const float *hv)
 	const int s = vw::lane();
 	double pb = (s == 0) ? 1.0 : 0.0;
 	unsigned hist = 0;
-	for (int n = 0; n < 25; n++) {
+#pragma unroll 1
+	for (int n = 0; n < 25; n++) {	/* once per burst: not unrolled, the kernel has to stay inside the instruction cache */
 		const float V = hv[n];
 		const int src1 = s ^ hcol(n);
 		const double p1 = vw::shfl(pb, src1);
@@ -263,6 +292,7 @@ VQ_COLD unsigned header_decode(const float *hv)
 	}
 	unsigned bits = 0, b = 1;
 	int st = 0;
+#pragma unroll 1
 	for (int n = 25; n > 0; n--) {
 		const unsigned h = vw::shfl(hist, st);
 		const unsigned bit = (h >> (n - 1)) & 1u;
@@ -291,7 +321,7 @@ struct ChanRegs {		/* warp-uniform working copy of the scalar state */
 	unsigned n_steps, n_syncs, n_syms;
 };
 
-VQ void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long end_dump, int chn, int Fr)
+VQ_RARE void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long end_dump, int chn, int Fr)
 {
 	const int lane = vw::lane();
 	unsigned slot = 0;
@@ -325,11 +355,14 @@ VQ void emit_block(const Vdl2KParams & kp, int ch, const ChanRegs & R, long long
 /* scratch of the idle-mode search (shared memory; the kernel lends it the idle TMA stages) */
 #define VDL2_PHT_LEN (VDL2_PHHIST + VDL2_TILE_DUMPS / 2 + 32)
 #define VDL2_CAND_CAP 192
+#define VDL2_CAND0_CAP 96	/* candidates among the first VDL2_PRE_SKIP steps of a speculatively screened tile */
+#define VDL2_PRE_SKIP 96	/* steps whose screen needs phases of the previous tile (64 + 8 rounded up to a batch) */
 #define VDL2_WIN_LEN 80
 struct IdleScratch {
 	float *pht;		/* [VDL2_PHT_LEN]: pht[0..63] = the 64 phases before the tile, then one per idle step */
 	float2 *vw;		/* [96]: differential phasors v_t = z_t conj(z_{t-4}), sliding window */
 	unsigned short *cand;	/* [VDL2_CAND_CAP]: steps that passed the screen */
+	unsigned short *cand0;	/* [VDL2_CAND0_CAP]: same for the head of a speculatively screened tile (idle_prepass) */
 	float2 *win;		/* [VDL2_WIN_LEN]: the dumps one batch of 32 steps filters (copied from the L2-resident stream) */
 };
 
@@ -380,7 +413,7 @@ VQ float2 cmul_conj(float2 a, float2 b)
  * ------------------------------------------------------------------------------------- */
 #define VDL2_SCREEN_THR2 62.0f
 
-VQ void idle_trigger(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, long long dump_base, int dT, float eT,
+template < bool TAPS > VQ_RARE void idle_trigger(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, long long dump_base, int dT, float eT,
 		     float pT, float p2T, float fT)
 {				/* d8psk.c:292-308 */
 	R.state = VDL2_ST_GETHEAD;
@@ -396,7 +429,7 @@ VQ void idle_trigger(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const
 	R.P1 = filt_phase_any(sd, dT, nclk);
 	R.perr = R.p2err = 500.f;
 	R.sync_dump = dump_base + dT;
-	if ((kp.taps & VDL2_TAP_SYNCS_BIT)) {
+	if ((TAPS && (kp.taps & VDL2_TAP_SYNCS_BIT))) {
 		if (vw::lane() == 0 && R.n_syncs < kp.cap_syncs) {
 			Vdl2SyncRec s;
 			s.dump = R.sync_dump;
@@ -410,37 +443,30 @@ VQ void idle_trigger(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const
 	}
 }
 
-VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, const IdleScratch & S, int nd,
-		 long long dump_base, int &pos, int &nph)
-{
+/* Pass A of the idle search for the steps of batches [b_begin, b_end): exact phase of every step into
+   ph[VDL2_PHHIST + k]; if `screen`, the correlation screen marks candidates (steps k >= k_cand0 only) in
+   cand[].  `have_hist`: ph[0..63] holds the 64 phases before the run and sd[] the 16 dumps before the tile;
+   without it (idle_prepass) the first steps produce garbage that the caller never uses. */
+VQ_PASSA int idle_passA(const float2 * sd, IdleScratch S, float *ph, int r, int p0, int N, int nd, int b_begin, int b_end, bool screen,
+		       bool have_hist, int k_cand0, unsigned short *cand, int cand_cap)
+{				/* out of line: three call sites, and the kernel has to stay inside the instruction cache.
+				   Returns the number of candidates (> cand_cap: the list overflowed) */
 	const int lane = vw::lane();
-	if (R.clk >= 8)
-		R.clk &= 7;	/* unreachable for finite input (clk < 8 whenever the burst clock was sane) */
-	const int c4 = R.clk >= 4;
-	const int p0 = pos + (c4 ? 0 : 1);	/* dump of the first step: a step every 2nd dump (d8psk.c:248-250) */
-	const int r = c4 ? R.clk - 4 : R.clk;	/* tap phase of every step of the run */
-	if (p0 >= nd) {
-		R.clk += 4 * (nd - pos);
-		pos = nd;
-		return;
-	}
-	const int N = ((nd - 1 - p0) >> 1) + 1;	/* steps in this run */
-	float *ph = S.pht + nph;	/* ph[0..63] = history, ph[64 + k] = phase of step k */
+	S.pht = vw::as_shared(S.pht);
+	S.vw = vw::as_shared(S.vw);
+	S.win = vw::as_shared(S.win);
+	ph = vw::as_shared(ph);
+	cand = vw::as_shared(cand);
+	int ncand = 0;
 	float m[17];
 #pragma unroll
 	for (int j = 0; j < 17; j++)
 		m[j] = c_tab.mflt[r + 4 * j];	/* r + 64 <= 67: zero padded */
-
-	const bool exact_only = (kp.taps & VDL2_TAP_STEPS_BIT) || (kp.flags & VDL2_FLAG_NO_SCREEN) || !(R.perr >= 4.0f) || N < 8;
-
-	/* ---- pass A: exact phase of every step; screen ---- */
-	int ncand = 0;
-	bool overflow = false;
 	float2 zlast = make_float2(1.f, 0.f);
-	if (!exact_only) {
+	if (screen && have_hist) {
 		float2 zA, zB;
-		vw::sincos(ph[lane], zA.y, zA.x);
-		vw::sincos(ph[32 + lane], zB.y, zB.x);
+		vw::sincos(ph[b_begin + lane], zA.y, zA.x);
+		vw::sincos(ph[b_begin + 32 + lane], zB.y, zB.x);
 		const float2 a4 = make_float2(vw::shfl_up(zA.x, 4), vw::shfl_up(zA.y, 4));
 		const float2 b4u = make_float2(vw::shfl_up(zB.x, 4), vw::shfl_up(zB.y, 4));
 		const float2 b4w = make_float2(vw::shfl(zA.x, (lane + 28) & 31), vw::shfl(zA.y, (lane + 28) & 31));
@@ -450,8 +476,8 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		vw::sync();
 	}
 	float2 wa, wb, wc;
-	win_fetch(sd, p0, VDL2_HIST + nd, wa, wb, wc);
-	for (int b0 = 0; b0 < N; b0 += 32) {
+	win_fetch(sd, p0 + 2 * b_begin, VDL2_HIST + nd, wa, wb, wc);
+	for (int b0 = b_begin; b0 < b_end; b0 += 32) {
 		const int k = b0 + lane;
 		/* the 79 dumps this batch filters, sd[p0 + 2*b0 .. +78], were fetched from L2 one batch ahead */
 		S.win[lane] = wa;
@@ -459,7 +485,7 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		if (lane < VDL2_WIN_LEN - 64)
 			S.win[lane + 64] = wc;
 		vw::sync();
-		if (b0 + 32 < N)
+		if (b0 + 32 < b_end)
 			win_fetch(sd, p0 + 2 * (b0 + 32), VDL2_HIST + nd, wa, wb, wc);
 		float sr = 1.f, si = 0.f;
 		if (k < N)
@@ -467,7 +493,7 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		const float P = vw::atan2(si, sr);
 		if (k < N)
 			ph[VDL2_PHHIST + k] = P;
-		if (!exact_only) {
+		if (screen) {
 			const float mag2 = vw::fma(sr, sr, si * si);
 			const bool ok = (mag2 > 1e-30f) && (mag2 < 1e30f);
 			const float rn = vw::rsqrt(ok ? mag2 : 1.f);
@@ -493,14 +519,12 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 			const float dx = B0.x + B2.y, dy = B0.y - B2.x;
 			const float sx = cx + 0.70710678f * (dx + dy), sy = cy + 0.70710678f * (dy - dx);
 			const float c2 = vw::fma(sx, sx, sy * sy);
-			const bool cand = (k < N) && (!ok || !(c2 < VDL2_SCREEN_THR2) || k >= N - 2);
-			const unsigned cm = vw::ballot(cand);
+			const bool cnd = (k < N) && (k >= k_cand0) && (!ok || !(c2 < VDL2_SCREEN_THR2) || k >= N - 2);
+			const unsigned cm = vw::ballot(cnd);
 			const int slot = ncand + vw::popc(cm & ((1u << lane) - 1u));
-			if (cand && slot < VDL2_CAND_CAP)
-				S.cand[slot] = (unsigned short)k;
+			if (cnd && slot < cand_cap)
+				cand[slot] = (unsigned short)k;
 			ncand += vw::popc(cm);
-			if (ncand > VDL2_CAND_CAP)
-				overflow = true;
 			/* slide the window by 32 steps */
 			const float2 w1 = S.vw[32 + lane], w2 = S.vw[64 + lane];
 			vw::sync();
@@ -509,14 +533,88 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		}
 		vw::sync();
 	}
+	return ncand;
+}
+
+/* Speculative pass A (see the kernel: it runs while the warp would otherwise wait for the previous tile of
+   its channel): demod_tile is entered once with `spec` set and a GUESS of the channel's tick clock at the
+   start of the tile in R.clk; idle_run then only runs pass A without history (phases of all but the first
+   steps, screen of all but the first VDL2_PRE_SKIP) and records what it assumed.  The real call verifies the
+   guess and falls back to the normal path otherwise.  One code path serves both so that pass A, the largest
+   loop of phase 2, exists once in the kernel (out of line it ran 8 % slower, twice inline it does not fit
+   the instruction cache). */
+struct IdlePre {
+	int valid, clk, ncand;
+	bool overflow;
+	int used;		/* set by idle_run when the speculative results were accepted (statistics) */
+};
+
+template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, const IdleScratch & S, int nd,
+		 long long dump_base, int &pos, int &nph, IdlePre & pre, bool spec)
+{
+	const int lane = vw::lane();
+	if (R.clk >= 8)
+		R.clk &= 7;	/* unreachable for finite input (clk < 8 whenever the burst clock was sane) */
+	const int c4 = R.clk >= 4;
+	const int p0 = pos + (c4 ? 0 : 1);	/* dump of the first step: a step every 2nd dump (d8psk.c:248-250) */
+	const int r = c4 ? R.clk - 4 : R.clk;	/* tap phase of every step of the run */
+	const bool use_pre = !spec && pre.valid && pos == 0 && nph == 0 && pre.clk == R.clk && R.perr >= 4.0f
+	    && !(TAPS && (kp.taps & VDL2_TAP_STEPS_BIT)) && !(TAPS && (kp.flags & VDL2_FLAG_NO_SCREEN));
+	pre.valid = 0;		/* a prepass covers the first run of the tile only */
+	if (use_pre)
+		pre.used = 1;
+	if (p0 >= nd) {
+		R.clk += 4 * (nd - pos);
+		pos = nd;
+		return;
+	}
+	const int N = ((nd - 1 - p0) >> 1) + 1;	/* steps in this run */
+	float *ph = S.pht + nph;	/* ph[0..63] = history, ph[64 + k] = phase of step k */
+
+	const bool exact_only = (TAPS && (kp.taps & VDL2_TAP_STEPS_BIT)) || (TAPS && (kp.flags & VDL2_FLAG_NO_SCREEN)) || !(R.perr >= 4.0f) || N < 8;
+
+	/* ---- pass A: exact phase of every step; screen ---- */
+	int ncand = 0, ncand0 = 0;
+	bool overflow = false;
+	if (spec && N < VDL2_PRE_SKIP + 32) {
+		pos = nd;	/* too short to be worth it: no speculation */
+		return;
+	}
+	{
+		/* one call site, three uses:
+		   spec     all batches, no history: candidates only from step VDL2_PRE_SKIP on;
+		   use_pre  the head of the tile again, now that the previous tile's dumps and phases are known;
+		   else     the plain full pass */
+		const int b_end = use_pre ? VDL2_PRE_SKIP : N;
+		const int nc = idle_passA(sd, S, ph, r, p0, N, nd, 0, b_end, spec || use_pre || !exact_only, !spec, spec ? VDL2_PRE_SKIP : 0,
+					  use_pre ? S.cand0 : S.cand, use_pre ? VDL2_CAND0_CAP : VDL2_CAND_CAP);
+		if (spec) {
+			pre.ncand = nc;
+			pre.overflow = nc > VDL2_CAND_CAP;
+			pre.clk = R.clk;
+			pre.valid = 1;
+			pos = nd;
+			return;
+		}
+		if (use_pre) {
+			ncand0 = nc;
+			ncand = pre.ncand;
+			overflow = pre.overflow || nc > VDL2_CAND0_CAP;
+		} else {
+			ncand = nc;
+			overflow = nc > VDL2_CAND_CAP;
+		}
+	}
 
 	/* ---- pass B: exact fit of the candidates, in time order, until the first err < 4 ---- */
 	int s0 = exact_only || overflow ? 0 : -1;	/* first step of the exact search; -1: no trigger possible in this run */
 	float eN1 = 0.f, eN2 = 0.f, fN1 = 0.f;
 	if (s0 < 0) {
-		for (int c0 = 0; c0 < ncand; c0 += 32) {
-			const bool have = c0 + lane < ncand;
-			const int k = have ? (int)S.cand[c0 + lane] : 0;
+		const int ntot = ncand0 + ncand;
+		for (int c0 = 0; c0 < ntot; c0 += 32) {
+			const int ci = c0 + lane;
+			const bool have = ci < ntot;
+			const int k = have ? (int)(ci < ncand0 ? S.cand0[ci] : S.cand[ci - ncand0]) : 0;
 			float err, fr;
 			sync_fit(ph + k, err, fr);
 			const unsigned hm = vw::ballot(have && err < 4.0f);
@@ -559,7 +657,7 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 		const bool trig = (lane < nb) && (perr_l < 4.0f) && (err > perr_l);
 		const unsigned tm = vw::ballot(trig);
 		const int K = tm ? vw::ffs(tm) : nb;	/* steps committed, trigger step included */
-		if ((kp.taps & VDL2_TAP_STEPS_BIT) && lane < K) {
+		if ((TAPS && (kp.taps & VDL2_TAP_STEPS_BIT)) && lane < K) {
 			const unsigned idx = R.n_steps + lane;
 			if (idx < kp.cap_steps) {
 				Vdl2StepRec s;
@@ -572,7 +670,7 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 				kp.tap_steps[(size_t) ch * kp.cap_steps + idx] = s;
 			}
 		}
-		R.n_steps += (kp.taps & VDL2_TAP_STEPS_BIT) ? K : 0;
+		R.n_steps += (TAPS && (kp.taps & VDL2_TAP_STEPS_BIT)) ? K : 0;
 		if (!tm) {
 			const float eL = vw::shfl(err, K - 1), fL = vw::shfl(fr, K - 1);
 			const float eP = vw::shfl(err, K >= 2 ? K - 2 : 0);
@@ -584,7 +682,7 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 			const float eT = vw::shfl(err, T), pT = vw::shfl(perr_l, T);
 			const float p2T = vw::shfl(p2err_l, T), fT = vw::shfl(pfr_l, T);
 			const int dT = p0 + 2 * (b0 + T);
-			idle_trigger(kp, ch, Fr, R, sd, dump_base, dT, eT, pT, p2T, fT);
+			idle_trigger < TAPS > (kp, ch, Fr, R, sd, dump_base, dT, eT, pT, p2T, fT);
 			nph += b0 + T + 1;	/* the Ph ring stops at the trigger step (d8psk.c:254-255) */
 			pos = dT + 1;
 			return;
@@ -595,8 +693,8 @@ VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const flo
 	R.clk = r;
 }
 
-VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, const IdleScratch & S, float *hv,
-		   int nd, long long dump_base, int &nph)
+template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, const IdleScratch & S, float *hv,
+		   int nd, long long dump_base, int &nph, IdlePre & pre, bool spec)
 {
 	const int lane = vw::lane();
 	int pos = 0;
@@ -605,7 +703,7 @@ VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R
 
 	while (pos < nd) {
 		if (R.state == VDL2_ST_WSYNC) {
-			idle_run(kp, ch, Fr, R, sd, S, nd, dump_base, pos, nph);
+			idle_run < TAPS > (kp, ch, Fr, R, sd, S, nd, dump_base, pos, nph, pre, spec);
 		} else {
 			/* ---- burst: up to 32 symbols at dumps ds0, ds0+8, ... (d8psk.c:314-332) ---- */
 			const int c = R.clk;
@@ -656,7 +754,7 @@ VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R
 			}
 			const float Plast = vw::shfl(Pn, nb - 1);
 
-			if ((kp.taps & VDL2_TAP_SYMS_BIT) && lane < nb) {
+			if ((TAPS && (kp.taps & VDL2_TAP_SYMS_BIT)) && lane < nb) {
 				const unsigned idx = R.n_syms + lane;
 				if (idx < kp.cap_syms) {
 					Vdl2SymRec s;
@@ -672,7 +770,7 @@ VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R
 					kp.tap_syms[(size_t) ch * kp.cap_syms + idx] = s;
 				}
 			}
-			R.n_syms += (kp.taps & VDL2_TAP_SYMS_BIT) ? nb : 0;
+			R.n_syms += (TAPS && (kp.taps & VDL2_TAP_SYMS_BIT)) ? nb : 0;
 
 			const int dl = ds0 + 8 * (nb - 1);	/* dump of the last symbol of the batch */
 			if (head) {
@@ -694,14 +792,20 @@ VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R
 					const unsigned len = revbits(w, 17);
 					R.nbrow = (int)(len / 1992u) + 1;
 					R.nlbyte = (int)((len % 1992u + 7u) / 8u);
+					long long idle_from = dump_base + dl + 1;	/* rejected header: idle again right away */
 					if (len < 96u || R.nbrow > 8) {
 						R.state = VDL2_ST_WSYNC;	/* d8psk.c:97-107 */
 					} else {
+						idle_from += 8LL * (burst_geom(R.nbrow, R.nlbyte).nsym - 9);	/* one symbol every 8 dumps */
 						R.state = VDL2_ST_GETDATA;
 						R.bytes_done = 0;
 						/* bits 25 and 26 are already payload (d8psk.c:117-123) */
 						R.bitacc = (hv[25] > 0.5f ? 1 : 0) | (hv[26] > 0.5f ? 2 : 0);
 						R.nbitacc = 2;
+					}
+					if (kp.state && lane == 0) {	/* forecast for the tiles after this burst (Vdl2ChanState.fc_*) */
+						kp.state[ch].fc_dump = idle_from;
+						kp.state[ch].fc_clk = r;
 					}
 				}
 			} else {

@@ -147,7 +147,7 @@ static void build_tables(Vdl2Tables & t, unsigned *sched_dump, const vdl2gpu * h
 				const int len = n + 1 - start, w0 = start % nco_n;
 				const int wl = (len == 24) ? w0 + 22 : VDL2_W8_PHASES + nshort++;
 				if (k < VDL2_DUMPS_PER_ROW)
-					sched_dump[k] = ((unsigned)(getenv("VDL2_TEST_ALIGN") ? (start & ~7) : start) << 16) | ((unsigned)wl << 8) | (unsigned)w0;
+					sched_dump[k] = ((unsigned)start << 16) | ((unsigned)wl << 8) | (unsigned)w0;
 				start = n + 1;
 				k++;
 			}
@@ -217,7 +217,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->dp4a = 0;
 	h->d_w8 = NULL;
 	if ((cfg->format == VDL2_FMT_CU8 || cfg->format == VDL2_FMT_CS8) && !(cfg->taps & VDL2_OPT_FLOAT_MIX) && nco_n + 24 <= VDL2_W8_PHASES
-	    && getenv("VDL2_DP4A")) {	/* work in progress: opt-in until the window variants land */
+	    && !getenv("VDL2_FLOAT_MIX")) {
 		int clk = 0, start = 0, ok = 1, nshort = 0;
 		for (int n = 0; n < h->row_samples; n++) {
 			clk += 21;
@@ -543,12 +543,12 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	const cuuint32_t estr[3] = { 1, 1, 1 };
 	CUresult r;
 	if (h->dp4a) {
-		/* one element = one IQ sample (2 bytes); a box = the 24 samples from the start of a dump, 32 rows; not
-		   swizzled (the 48-byte pitch is conflict free); samples past the end of a row read as zero */
+		/* one element = one IQ sample (2 bytes); a box = 32 samples x 32 rows from the 16-byte boundary at or before the
+		   start of a dump (TMA boxes must start 16-byte aligned), 64B-swizzled; samples past the end of a row read as zero */
 		const cuuint64_t dims[3] = { (cuuint64_t) h->row_samples, (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
-		const cuuint32_t box[3] = { 24, 32, 1 };
+		const cuuint32_t box[3] = { 32, 32, 1 };
 		r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)base, dims, strides, box, estr,
-						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
 						    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	} else {
 		const cuuint64_t dims[3] = { (cuuint64_t) (h->row_bytes / 4), (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
@@ -586,6 +586,8 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.dropped = h->d_dropped;
 	kp.taps = h->cfg.taps & 15u;
 	kp.flags = (h->cfg.taps & VDL2_OPT_EXACT_IDLE) ? VDL2_FLAG_NO_SCREEN : 0u;
+	if (getenv("VDL2_NO_PREPASS"))	/* A/B switch for tools/ab_probe.sh */
+		kp.flags |= VDL2_FLAG_NO_PREPASS;
 	kp.tap_dumps = h->d_tap_dumps;
 	kp.tap_steps = h->d_tap_steps;
 	kp.tap_syncs = h->d_tap_syncs;
@@ -596,6 +598,13 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.cap_syms = h->cap_syms;
 
 	CK(h, cudaMemsetAsync(h->d_ticket, 0, 4, h->stream));
+	if (getenv("VDL2_PRE_STATS")) {	/* debug: outcome counters of the speculative pass A of the previous launch */
+		unsigned c[4];
+		cudaStreamSynchronize(h->stream);
+		cudaMemcpy(c, h->d_ticket + 12, sizeof c, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "vdl2gpu: prepass used %u wasted %u idle-without %u burst-start %u\n", c[0], c[1], c[2], c[3]);
+		cudaMemset(h->d_ticket + 12, 0, sizeof c);
+	}
 	CK(h, cudaMemsetAsync(h->d_progress, 0, sizeof(int) * h->cfg.nch, h->stream));
 	const long long items = (long long)kp.ntiles * kp.nch;
 	const int grid = (int)std::min < long long >(items, h->grid);

@@ -359,20 +359,44 @@ template < int FMT > __device__ __forceinline__ void chunk_bound(int E, MixAcc &
  *     applied per dump from the dcorr table (built in double on the host);
  *   - the six int32 sums are exact; they are combined in fp32 at the dump close (relative error 1e-7,
  *     the weight quantisation contributes < 1e-7 of the dump rms: tests/test_gpu_parity.py).
- * Dump boundaries never fall inside a word because the TMA boxes are DUMP ALIGNED: the tensor map has
- * 2-byte elements (one IQ sample), box k = 24 samples x 32 rows starting at the first sample of dump k
- * (no swizzle: the 48-byte row pitch is already conflict free for LDS.128).  A 23-sample dump reads one
- * sample too many; its last table entry has zero weights for it.
+ * Dump boundaries never fall inside a dot product because the TMA boxes follow the DUMPS: the tensor map
+ * has 2-byte elements (one IQ sample); box k = the 32 samples x 32 rows starting at the 8-sample (16-byte,
+ * the TMA alignment rule) boundary at or before the first sample of dump k, 64B-swizzled so that LDS.128 is
+ * conflict free.  The dump begins 0..7 samples into its window: the word part of that offset selects one of
+ * four unrolled bodies (registers cannot be indexed dynamically), the half-word part is a PRMT selector.
+ * A 23-sample dump reads one sample too many; its last table entry has zero weights for it.
  * Dumps are transposed through a small shared tile so that the scratch stores are coalesced (one
  * STG.64 per dump used to touch 32 sectors).
  */
 #define D8_NST VDL2_D8_NST
-#define D8_STAGE 1536
+#define D8_STAGE 2048		/* 32 rows x 64 bytes */
 #define D8_TPITCH 9		/* float2 per row of the transpose tile: 8 dumps + 1 pad (conflict-free STS.64) */
 
 __device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c)
 {
 	return __dp4a((int)a, (int)b, c);
+}
+
+/* One dump of one row: d[0..15] = the 64-byte window holding it, the dump starts WO words + (2 bytes if the
+   selectors say so) into the window.  WO is a template parameter because registers cannot be indexed
+   dynamically; the half-word shift and the (I,Q) -> (Q,I) swap are one PRMT each with run-time selectors. */
+template < int FMT, int WO > __device__ __forceinline__ void dump_dp4a(const uint32_t(&d)[16], uint32_t sel_e, uint32_t sel_s,
+									 const uint4 * wt, const uint4 * wlast, int (&acc)[6])
+{
+	const uint32_t KR = (FMT == VDL2_FMT_CU8) ? 0x7F807F80u : 0xFF00FF00u;	/* I -> signed, Q -> ~signed */
+	const uint32_t KS = (FMT == VDL2_FMT_CU8) ? 0x80808080u : 0u;
+#pragma unroll
+	for (int p = 0; p < 12; p++) {
+		const uint4 W = (p == 11) ? *wlast : wt[2 * p];
+		const uint32_t xr = __byte_perm(d[WO + p], d[WO + p + 1], sel_e) ^ KR;
+		const uint32_t xs = __byte_perm(d[WO + p], d[WO + p + 1], sel_s) ^ KS;
+		acc[0] = dp4a_ss(xr, W.x, acc[0]);
+		acc[3] = dp4a_ss(xs, W.x, acc[3]);
+		acc[1] = dp4a_ss(xr, W.y, acc[1]);
+		acc[4] = dp4a_ss(xs, W.y, acc[4]);
+		acc[2] = dp4a_ss(xr, W.z, acc[2]);
+		acc[5] = dp4a_ss(xs, W.z, acc[5]);
+	}
 }
 
 template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtensorMap * tmap, const Vdl2KParams & kp, unsigned char *stage0,
@@ -382,55 +406,46 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
 {
 	const int lane = threadIdx.x;
 	const unsigned *sched = c_tab.sched_slots[kp.sched_slot];
-	const uint32_t KR = (FMT == VDL2_FMT_CU8) ? 0x7F807F80u : 0xFF00FF00u;	/* I -> signed, Q -> ~signed */
-	const uint32_t KS = (FMT == VDL2_FMT_CU8) ? 0x80808080u : 0u;
-	const unsigned char *rowp = stage0 + lane * 48;
-	int st = 0;		/* stage of the dump whose data are being loaded */
-	mbar_wait(smem_u32(bars), phases & 1u);
-	phases ^= 1u;
-	uint4 n0 = *reinterpret_cast < const uint4 * >(rowp);
-	uint4 n1 = *reinterpret_cast < const uint4 * >(rowp + 16);
-	uint4 n2 = *reinterpret_cast < const uint4 * >(rowp + 32);
+	/* 64B-swizzled box: 16-byte chunk c of row r sits at r*64 + ((c ^ ((r >> 1) & 3)) << 4) */
+	const uint32_t sw = (uint32_t) (lane >> 1) & 3u;
+	const unsigned char *rowp = stage0 + lane * 64;
+	const uint32_t o0 = (0u ^ sw) << 4, o1 = (1u ^ sw) << 4, o2 = (2u ^ sw) << 4, o3 = (3u ^ sw) << 4;
+	int st = 0;
 	float4 dcn = __ldg(dcorr);
-#pragma unroll 2
+#pragma unroll 1
 	for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
-		const uint32_t d[12] = { n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w };
 		const float4 dc = dcn;
 		const unsigned sk = sched[dk];
-		const int cur = st;
-		if (dk + 1 < VDL2_DUMPS_PER_ROW) {	/* data of the next dump: in registers before this one is mixed */
-			st = (st + 1 == D8_NST) ? 0 : st + 1;
-			mbar_wait(smem_u32(bars + st), (phases >> st) & 1u);
-			phases ^= 1u << st;
-			const unsigned char *p = rowp + st * D8_STAGE;
-			n0 = *reinterpret_cast < const uint4 * >(p);
-			n1 = *reinterpret_cast < const uint4 * >(p + 16);
-			n2 = *reinterpret_cast < const uint4 * >(p + 32);
-			dcn = __ldg(dcorr + dk + 1);
-		}
+		dcn = __ldg(dcorr + (dk + 1 < VDL2_DUMPS_PER_ROW ? dk + 1 : dk));
+		mbar_wait(smem_u32(bars + st), (phases >> st) & 1u);
+		phases ^= 1u << st;
+		const unsigned char *p = rowp + st * D8_STAGE;
+		const uint4 v0 = *reinterpret_cast < const uint4 * >(p + o0);
+		const uint4 v1 = *reinterpret_cast < const uint4 * >(p + o1);
+		const uint4 v2 = *reinterpret_cast < const uint4 * >(p + o2);
+		const uint4 v3 = *reinterpret_cast < const uint4 * >(p + o3);
+		const uint32_t d[16] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w };
+		const unsigned o = (sk >> 16) & 7u;	/* first sample of the dump inside the window */
+		const uint32_t sel_e = (o & 1u) ? 0x5432u : 0x3210u, sel_s = (o & 1u) ? 0x4523u : 0x2301u;
 		const uint4 *wt = w8 + (sk & 255u);
-		int re2 = 0, re1 = 0, re0 = 0, im2 = 0, im1 = 0, im0 = 0;
-#pragma unroll
-		for (int p = 0; p < 12; p++) {
-			const uint4 W = (p == 11) ? w8[(sk >> 8) & 255u] : wt[2 * p];
-			const uint32_t xr = d[p] ^ KR;
-			const uint32_t xs = __byte_perm(d[p], 0u, 0x2301) ^ KS;
-			re2 = dp4a_ss(xr, W.x, re2);
-			im2 = dp4a_ss(xs, W.x, im2);
-			re1 = dp4a_ss(xr, W.y, re1);
-			im1 = dp4a_ss(xs, W.y, im1);
-			re0 = dp4a_ss(xr, W.z, re0);
-			im0 = dp4a_ss(xs, W.z, im0);
+		const uint4 *wlast = w8 + ((sk >> 8) & 255u);
+		int acc[6] = { 0, 0, 0, 0, 0, 0 };
+		switch (o >> 1) {
+		case 0: dump_dp4a < FMT, 0 > (d, sel_e, sel_s, wt, wlast, acc); break;
+		case 1: dump_dp4a < FMT, 1 > (d, sel_e, sel_s, wt, wlast, acc); break;
+		case 2: dump_dp4a < FMT, 2 > (d, sel_e, sel_s, wt, wlast, acc); break;
+		default: dump_dp4a < FMT, 3 > (d, sel_e, sel_s, wt, wlast, acc); break;
 		}
-		const float fr = fmaf((float)re2, 65536.f, fmaf((float)re1, 256.f, (float)re0));
-		const float fi = fmaf((float)im2, 65536.f, fmaf((float)im1, 256.f, (float)im0));
+		const float fr = fmaf((float)acc[0], 65536.f, fmaf((float)acc[1], 256.f, (float)acc[2]));
+		const float fi = fmaf((float)acc[3], 65536.f, fmaf((float)acc[4], 256.f, (float)acc[5]));
 		tile[lane * D8_TPITCH + (dk & 7)] = ffma2(make_float2(fr, fi), make_float2(dc.x, dc.y), make_float2(dc.z, dc.w));
-		__syncwarp();	/* every lane has consumed the stage dump dk came from */
+		__syncwarp();	/* every lane has consumed the stage */
 		if (lane == 0 && dk + D8_NST < VDL2_DUMPS_PER_ROW) {
-			const uint32_t bar = smem_u32(bars + cur);
+			const uint32_t bar = smem_u32(bars + st);
 			mbar_expect_tx(bar, D8_STAGE);
-			tma_load_3d(smem_u32(stage0 + cur * D8_STAGE), tmap, bar, (int)(sched[dk + D8_NST] >> 16), row0, stream, l2pol);
+			tma_load_3d(smem_u32(stage0 + st * D8_STAGE), tmap, bar, (int)((sched[dk + D8_NST] >> 16) & ~7u), row0, stream, l2pol);
 		}
+		st = (st + 1 == D8_NST) ? 0 : st + 1;
 		if ((dk & 7) == 7 || dk == VDL2_DUMPS_PER_ROW - 1) {
 			/* 8 (last group: 4) dumps x 32 rows -> scratch, 64 contiguous bytes per row */
 			const int k0 = dk & ~7, ng = dk - k0 + 1;
@@ -448,9 +463,15 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template < int FMT, bool DP > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
+template < int FMT, bool DP, bool TAPS > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
+#ifdef VDL2_KP_BYVALUE
 vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
+#else
+vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Vdl2KParams kp)
+#endif
 {
+	/* TAPS = false: production launches (no observation taps, no debug flags) run an instantiation in which all
+	   of that code is compiled out -- the kernel has to stay inside the instruction cache */
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const int lane = threadIdx.x;
 	unsigned char *stage0 = smem;
@@ -468,7 +489,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 	scr.vw = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4);
 	scr.win = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
 	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8);
-	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + VDL2_CAND_CAP * 2 <= STAGES_BYTES,
+	scr.cand0 = scr.cand + VDL2_CAND_CAP;
+	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + (VDL2_CAND_CAP + VDL2_CAND0_CAP) * 2 <= STAGES_BYTES,
 		      "phase 2 scratch must fit the stages");
 	static_assert(NBAR <= 8, "mbarriers live in 64 bytes");
 
@@ -512,7 +534,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 				for (int b = 0; b < D8_NST; b++) {
 					const uint32_t bar = smem_u32(bars + b);
 					mbar_expect_tx(bar, D8_STAGE);
-					tma_load_3d(smem_u32(stage0 + b * D8_STAGE), &tmap, bar, (int)(c_tab.sched_slots[kp.sched_slot][b] >> 16), row0,
+					tma_load_3d(smem_u32(stage0 + b * D8_STAGE), &tmap, bar, (int)((c_tab.sched_slots[kp.sched_slot][b] >> 16) & ~7u), row0,
 						    stream, l2pol);
 				}
 			}
@@ -601,58 +623,92 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 		__threadfence_block();
 		__syncwarp();
 
-		/* ---- wait for the previous tile of this channel, load its state ---- */
-		if (lane == 0) {
-			const volatile int *pr = kp.progress + ch;
-			while (*pr < tile)
-				__nanosleep(200);
-		}
-		__syncwarp();
-		__threadfence();
+		/* ---- two stages through ONE instance of the demodulator code:
+		   stage 0 (speculative, see IdlePre): while the previous tile of this channel is still being demodulated
+		     elsewhere, pass A of the idle search from the channel's published forecast.  Without it the per-channel
+		     chain of phase 2 executions is the critical path of the launch;
+		   stage 1: wait for the previous tile, load its state, demodulate. ---- */
 		Vdl2ChanState *gs = kp.state + ch;
-		if (lane < VDL2_HIST)
-			__stcg(sd + lane, make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane)));
-		scr.pht[lane] = __ldcg(gs->ph + lane);
-		scr.pht[lane + 32] = __ldcg(gs->ph + lane + 32);
-		if (lane < 28)
-			hv[lane] = __ldcg(gs->hv + lane);
+		IdlePre pre;
+		pre.valid = 0;
+		pre.used = 0;
 		ChanRegs R;
-		R.perr = __ldcg(&gs->perr);
-		R.p2err = __ldcg(&gs->p2err);
-		R.pfr = __ldcg(&gs->pfr);
-		R.df = __ldcg(&gs->df);
-		R.P1 = __ldcg(&gs->P1);
-		R.ppm = __ldcg(&gs->ppm);
-		R.clk = __ldcg(&gs->clk);
-		R.state = __ldcg(&gs->state);
-		R.symidx = __ldcg(&gs->symidx);
-		R.nbrow = __ldcg(&gs->nbrow);
-		R.nlbyte = __ldcg(&gs->nlbyte);
-		R.bytes_done = __ldcg(&gs->bytes_done);
-		R.bitacc = __ldcg(&gs->bitacc);
-		R.nbitacc = __ldcg(&gs->nbitacc);
-		R.sync_dump = __ldcg(&gs->sync_dump);
-		R.n_steps = __ldcg(&gs->n_steps);
-		R.n_syncs = __ldcg(&gs->n_syncs);
-		R.n_syms = __ldcg(&gs->n_syms);
-		__threadfence_block();
-		unsigned n_dumps = __ldcg(&gs->n_dumps);
-		const int chn = __ldcg(&gs->chn), Fr = __ldcg(&gs->Fr);
-		__syncwarp();
-
+		unsigned n_dumps = 0;
+		int chn = 0, Fr = 0, nph = 0, had_pre = 0, idle_at_start = 0;
 		const long long dump_base = kp.dump_base + (long long)row0 * VDL2_DUMPS_PER_ROW;
-		if (kp.taps & VDL2_TAP_DUMPS_BIT) {
-			float2 *dst = kp.tap_dumps + (size_t) ch * kp.cap_dumps;
-			for (int i = lane; i < nd; i += 32)
-				if (n_dumps + i < kp.cap_dumps)
-					dst[n_dumps + i] = __ldcg(sd + VDL2_HIST + i);
-			n_dumps += nd;
+#pragma unroll 1
+		for (int stage = 0; stage < 2; stage++) {
+			const bool spec = (stage == 0);
+			if (spec) {
+				if (TAPS && ((kp.taps & VDL2_TAP_STEPS_BIT) || (kp.flags & (VDL2_FLAG_NO_SCREEN | VDL2_FLAG_NO_PREPASS))))
+					continue;
+				/* the channel's forecast (Vdl2ChanState.fc_*), read without synchronisation: idle_run verifies the guess */
+				const long long F = __ldcg(&gs->fc_dump);
+				const int c = __ldcg(&gs->fc_clk) & 7;
+				if (F > dump_base)
+					continue;	/* as far as is known the tile starts inside a burst */
+				const int s = (c >= 4) ? 0 : 1;	/* dump F + s is the first idle step; then every 2nd dump */
+				const long long e = dump_base - F - s;
+				memset(&R, 0, sizeof R);
+				R.clk = (c & 3) + ((e >= 0 && (e & 1LL) == 0) ? 4 : 0);
+				R.state = VDL2_ST_WSYNC;
+				R.perr = 100.f;
+			} else {
+				/* wait for the previous tile of this channel, load its state */
+				if (lane == 0) {
+					const volatile int *pr = kp.progress + ch;
+					while (*pr < tile)
+						__nanosleep(200);
+				}
+				__syncwarp();
+				__threadfence();
+				if (lane < VDL2_HIST)
+					__stcg(sd + lane, make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane)));
+				scr.pht[lane] = __ldcg(gs->ph + lane);
+				scr.pht[lane + 32] = __ldcg(gs->ph + lane + 32);
+				if (lane < 28)
+					hv[lane] = __ldcg(gs->hv + lane);
+				R.perr = __ldcg(&gs->perr);
+				R.p2err = __ldcg(&gs->p2err);
+				R.pfr = __ldcg(&gs->pfr);
+				R.df = __ldcg(&gs->df);
+				R.P1 = __ldcg(&gs->P1);
+				R.ppm = __ldcg(&gs->ppm);
+				R.clk = __ldcg(&gs->clk);
+				R.state = __ldcg(&gs->state);
+				R.symidx = __ldcg(&gs->symidx);
+				R.nbrow = __ldcg(&gs->nbrow);
+				R.nlbyte = __ldcg(&gs->nlbyte);
+				R.bytes_done = __ldcg(&gs->bytes_done);
+				R.bitacc = __ldcg(&gs->bitacc);
+				R.nbitacc = __ldcg(&gs->nbitacc);
+				R.sync_dump = __ldcg(&gs->sync_dump);
+				R.n_steps = __ldcg(&gs->n_steps);
+				R.n_syncs = __ldcg(&gs->n_syncs);
+				R.n_syms = __ldcg(&gs->n_syms);
+				__threadfence_block();
+				n_dumps = __ldcg(&gs->n_dumps);
+				chn = __ldcg(&gs->chn);
+				Fr = __ldcg(&gs->Fr);
+				__syncwarp();
+				if (TAPS && (kp.taps & VDL2_TAP_DUMPS_BIT)) {
+					float2 *dst = kp.tap_dumps + (size_t) ch * kp.cap_dumps;
+					for (int i = lane; i < nd; i += 32)
+						if (n_dumps + i < kp.cap_dumps)
+							dst[n_dumps + i] = __ldcg(sd + VDL2_HIST + i);
+					n_dumps += nd;
+				}
+				had_pre = pre.valid;
+				idle_at_start = (R.state == VDL2_ST_WSYNC);
+			}
+			nph = 0;
+			demod_tile < TAPS > (kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph, pre, spec);
+			__syncwarp();
 		}
-
-		/* ---- phase 2 ---- */
-		int nph = 0;
-		demod_tile(kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph);
-		__syncwarp();
+#ifndef VDL2_NO_STATS
+		if (lane == 0)	/* statistics: 0 speculation used, 1 wasted, 2 idle tile without one, 3 tile that starts inside a burst */
+			atomicAdd(kp.ticket + 12 + (pre.used ? 0 : (had_pre ? 1 : (idle_at_start ? 2 : 3))), 1u);
+#endif
 
 		/* ---- store state, release the channel ---- */
 		if (lane < VDL2_HIST) {
@@ -684,6 +740,10 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams
 			gs->n_syncs = R.n_syncs;
 			gs->n_syms = R.n_syms;
 			gs->n_dumps = n_dumps;
+			if (R.state == VDL2_ST_WSYNC) {
+				gs->fc_dump = dump_base + nd;
+				gs->fc_clk = R.clk;
+			}
 		}
 		__threadfence();
 		__syncwarp();
@@ -703,13 +763,25 @@ extern "C" int vdl2_kernel_smem_bytes(int nco_entries, int dp4a)
 	return VDL2_NSTAGE * STAGE_BYTES + 64 + 32 * 4 + nco_entries * 16;
 }
 
-template < int FMT, bool DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+template < int FMT, bool DP, bool TAPS > static cudaError_t launch_fmt2(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem,
+									 cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess)
 		return e;
-	vdl2::vdl2_frontend_kernel < FMT, DP > <<<grid, 32, smem, st >>> (tmap, kp);
+	vdl2::vdl2_frontend_kernel < FMT, DP, TAPS > <<<grid, 32, smem, st >>> (tmap, kp);
 	return cudaGetLastError();
+}
+
+template < int FMT, bool DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+{
+#ifdef VDL2_ALWAYS_TAPS
+	if (true)
+#else
+	if (kp.taps || kp.flags)
+#endif
+		return launch_fmt2 < FMT, DP, true > (tmap, kp, grid, smem, st);
+	return launch_fmt2 < FMT, DP, false > (tmap, kp, grid, smem, st);
 }
 
 extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream)
@@ -735,8 +807,15 @@ extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl
 
 template < int FMT, bool DP > static cudaError_t occ_fmt(int smem, int *n)
 {
-	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, vdl2::vdl2_frontend_kernel < FMT, DP >, 32, smem);
+	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	int a = 0, b = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, vdl2::vdl2_frontend_kernel < FMT, DP, true >, 32, smem);
+	if (e != cudaSuccess)
+		return e;
+	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, vdl2::vdl2_frontend_kernel < FMT, DP, false >, 32, smem);
+	*n = a < b ? a : b;	/* the per-warp scratch is sized from this: one grid size for both instantiations */
+	return e;
 }
 
 extern "C" int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm)
