@@ -157,6 +157,52 @@ class Oracle:
         return int(self.lib.orc_ndump(self.h))
 
 
+FRAME_DT = np.dtype([("block", "<i4"), ("len", "<i4"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"), ("pad", "<i4"),
+                     ("sync_dump", "<i8"), ("hdata", "u1", (2016,))])
+BLKSTAT_DT = np.dtype([("rs", "i1", (8,)), ("nbytes", "<i4"), ("nframes", "<i4")])
+assert FRAME_DT.itemsize == 2048 and BLKSTAT_DT.itemsize == 16
+_LINK_PATHS = {"port": os.path.join(HERE, "libvdl2linkport.so"), "ref": os.path.join(HERE, "_ref", "libvdl2linkref.so")}
+_LINK_LIBS: dict = {}
+
+
+def link_available(kind: str) -> bool:
+    return os.path.exists(_LINK_PATHS[kind])
+
+
+def _link_lib(kind: str):
+    if kind not in _LINK_LIBS:
+        path = _LINK_PATHS[kind]
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"oracle library {path} missing (run `make -C oracle`)")
+        lib = C.CDLL(path)
+        lib.orc_link_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        lib.orc_link_time.restype = C.c_double
+        lib.orc_link_time.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _LINK_LIBS[kind] = lib
+    return _LINK_LIBS[kind]
+
+
+def link_decode(kind: str, blocks: np.ndarray):
+    """Block pipeline behind the demodulator (blk_thread, vdlm2.c:84-161) on the CPU: returns
+    (frames, per-block stats, data rows after rs())."""
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DT)
+    n = len(blocks)
+    frames = np.zeros(max(4 * n, 16), FRAME_DT)
+    stats = np.zeros(n, BLKSTAT_DT)
+    rows = np.zeros((n, 8, 255), np.uint8)
+    nf = C.c_int(0)
+    rc = _link_lib(kind).orc_link_decode(blocks.ctypes.data_as(C.c_void_p), n, frames.ctypes.data_as(C.c_void_p), len(frames),
+                                         C.byref(nf), stats.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError("orc_link_decode: frame buffer overflow")
+    return frames[:nf.value], stats, rows
+
+
+def link_time(kind: str, blocks: np.ndarray, reps: int) -> float:
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DT)
+    return float(_link_lib(kind).orc_link_time(blocks.ctypes.data_as(C.c_void_p), len(blocks), reps))
+
+
 def time_cu8(kind: str, iq: np.ndarray, reps: int, Fr=136_975_000, Fo=-50_000, fs=2_000_000, sdrclk=500) -> float:
     """Seconds for `reps` passes of one private channel over `iq` (taps off); GIL released."""
     lib = load(kind)
