@@ -6,8 +6,9 @@
  *   NCO mix + integrate-and-dump d8psk.c:343-382 (rcv_thread)
  *   interpolating filter, sync fit, timing, D8PSK slicer   d8psk.c:219-333
  *   soft demap, descrambler, header decode, de-interleave  d8psk.c:54-217, viterbi.c:37-96
- * up to the hand-off of a completed msgblk_t (decodeVdlm2(), vdlm2.c:189).
- * Everything downstream (rs.c, crc.c, out*.c) stays host code of the reference.
+ * up to the hand-off of a completed msgblk_t (decodeVdlm2(), vdlm2.c:189), and -- optionally, the next row of
+ * the scope table -- the block pipeline behind it (blk_thread, vdlm2.c:84-161: rs.c, HDLC, crc.c) up to the
+ * call of out().  Everything downstream (out*.c, label.c, cJSON) stays host code of the reference.
  *
  * The reference has no plugin API: the seam is the object d8psk.o (vdlm2.h:113-114,128).
  * Two layers are exported by libvdl2gpu.so:
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VDL2_ABI_VERSION 1
+#define VDL2_ABI_VERSION 2
 
 /* input sample formats; CU8 is what rtl.c receives (rtl.c:287-289: x - 127.37f),
    CF32 is the already converted Cbuff of the reference (vdlm2.h:89),
@@ -122,6 +123,9 @@ typedef struct {
 	int n_sm;
 	int grid;			/* persistent warps launched */
 	int smem_bytes;			/* dynamic shared memory per warp-CTA */
+	float last_link_ms;		/* device time of the last block-pipeline launch */
+	uint32_t link_launches;
+	uint64_t frames_out;
 } vdl2_stats_t;
 
 typedef struct vdl2gpu vdl2gpu_t;
@@ -151,6 +155,35 @@ int vdl2_read_dumps(vdl2gpu_t * h, int ch, float *iq_out, size_t max, size_t *n_
 int vdl2_read_steps(vdl2gpu_t * h, int ch, vdl2_step_t * out, size_t max, size_t *n_out);
 int vdl2_read_syncs(vdl2gpu_t * h, int ch, vdl2_sync_t * out, size_t max, size_t *n_out);
 int vdl2_read_syms(vdl2gpu_t * h, int ch, vdl2_sym_t * out, size_t max, size_t *n_out);
+
+/* ---- block pipeline behind the demodulator (blk_thread, vdlm2.c:84-161):
+   per row rs() (rs.c:81-291), HDLC bit un-stuffing, flag framing, FCS16 check (check_frame, vdlm2.c:40-61).
+   A frame is exactly what the reference passes to out(blk, hdata, l) (vdlm2.h:134). ---- */
+typedef struct {
+	int32_t block;		/* index into the blocks of the same call */
+	int32_t len;		/* l: bytes in hdata including both flags */
+	int32_t chn, Fr;	/* copied from the block */
+	float ppm;
+	int32_t pad;
+	int64_t sync_dump;
+	uint8_t hdata[2016];
+} vdl2_frame_t;			/* 2048 bytes */
+
+typedef struct {
+	int8_t rs[8];		/* rs() result per row: symbols corrected, -1 uncorrectable (the reference ignores it) */
+	int32_t nbytes;		/* un-stuffed bytes consumed into hdata[] at the end of the block */
+	int32_t nframes;	/* frames that passed check_frame() */
+} vdl2_blkstat_t;
+
+/* blocks from host memory -> frames, in (block, position) order.  stats (nblocks) and rows_after
+   (nblocks * 8 * 255 bytes: data[][] after the rs() calls) may be NULL. */
+int vdl2_link_decode(vdl2gpu_t * h, const vdl2_block_t * blocks, int nblocks, vdl2_frame_t * frames, int max_frames, int *n_frames,
+		     vdl2_blkstat_t * stats, uint8_t * rows_after);
+/* like vdl2_drain_blocks, but the completed blocks go through the block pipeline ON THE DEVICE first (no
+   round trip): returns the frames and, if blocks != NULL, the blocks themselves (oldest trigger first;
+   frame.block indexes them) */
+int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int *n_frames, vdl2_block_t * blocks, int max_blocks,
+		      int *n_blocks);
 
 int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
 /* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */

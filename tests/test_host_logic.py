@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = api.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vdl2_abi_version() == 1
+    assert lib.vdl2_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure():

@@ -33,6 +33,11 @@ SYM_DT = np.dtype([("dump", "<i8"), ("D", "<f4"), ("P", "<f4"), ("gi", "<i4"), (
 BLOCK_DT = np.dtype([("sync_dump", "<i8"), ("end_dump", "<i8"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"),
                      ("nbrow", "<i4"), ("nlbyte", "<i4"), ("data", "u1", (8, 255)), ("pad", "u1", (4,))])
 assert BLOCK_DT.itemsize == 2080
+# what the reference hands to out(blk, hdata, l) (vdlm2.h:134) after rs(), HDLC un-stuffing and the FCS check
+FRAME_DT = np.dtype([("block", "<i4"), ("len", "<i4"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"), ("pad", "<i4"),
+                     ("sync_dump", "<i8"), ("hdata", "u1", (2016,))])
+BLKSTAT_DT = np.dtype([("rs", "i1", (8,)), ("nbytes", "<i4"), ("nframes", "<i4")])
+assert FRAME_DT.itemsize == 2048 and BLKSTAT_DT.itemsize == 16
 
 
 class ChanParam(C.Structure):  # thread_param_t, vdlm2.h:49-52
@@ -48,12 +53,14 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("samples_in", C.c_uint64), ("samples_done", C.c_uint64),
                 ("blocks_out", C.c_uint64), ("blocks_dropped", C.c_uint64), ("last_kernel_ms", C.c_float),
-                ("n_sm", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int)]
+                ("n_sm", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int), ("last_link_ms", C.c_float),
+                ("link_launches", C.c_uint32), ("frames_out", C.c_uint64)]
 
 
 EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
-           "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream"]
+           "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
+           "vdl2_drain_frames"]
 
 _lib = None
 
@@ -79,6 +86,8 @@ def load_library():
     for f in ("vdl2_read_dumps", "vdl2_read_steps", "vdl2_read_syncs", "vdl2_read_syms"):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.vdl2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.vdl2_link_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    lib.vdl2_drain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.vdl2_cuda_stream.restype = C.c_void_p
     lib.vdl2_cuda_stream.argtypes = [C.c_void_p]
     _lib = lib
@@ -156,6 +165,29 @@ class Vdl2Gpu:
         n = C.c_int(0)
         self._check(self.lib.vdl2_drain_blocks(self.h, out.ctypes.data_as(C.c_void_p), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+    def link_decode(self, blocks: np.ndarray, want_rows: bool = True):
+        """Block pipeline behind the demodulator (blk_thread, vdlm2.c:84-161) on the GPU for blocks in host memory:
+        returns (frames, per-block stats, data rows after rs())."""
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DT)
+        n = len(blocks)
+        frames = np.zeros(max(4 * n, 16), FRAME_DT)
+        stats = np.zeros(n, BLKSTAT_DT)
+        rows = np.zeros((n, 8, 255), np.uint8) if want_rows else None
+        nf = C.c_int(0)
+        self._check(self.lib.vdl2_link_decode(self.h, blocks.ctypes.data_as(C.c_void_p), n, frames.ctypes.data_as(C.c_void_p),
+                                              len(frames), C.byref(nf), stats.ctypes.data_as(C.c_void_p),
+                                              rows.ctypes.data_as(C.c_void_p) if want_rows else None))
+        return frames[:nf.value].copy(), stats, rows
+
+    def drain_frames(self):
+        """Completed blocks -> block pipeline on the device -> (frames, blocks); frame['block'] indexes blocks."""
+        blocks = np.zeros(self._cap_blocks, dtype=BLOCK_DT)
+        frames = np.zeros(max(2 * self._cap_blocks, 16), FRAME_DT)
+        nf, nb = C.c_int(0), C.c_int(0)
+        self._check(self.lib.vdl2_drain_frames(self.h, frames.ctypes.data_as(C.c_void_p), len(frames), C.byref(nf),
+                                               blocks.ctypes.data_as(C.c_void_p), len(blocks), C.byref(nb)))
+        return frames[:nf.value].copy(), blocks[:nb.value].copy()
 
     def _read(self, fn, ch, dt, cap):
         out = np.zeros(cap, dtype=dt)

@@ -23,12 +23,15 @@
 #include <string>
 #include <vector>
 #include "vdl2_kernel.h"
+#include "vdl2_link.h"
 #include "vdl2_tables.h"
 
 static_assert(sizeof(Vdl2BlockRec) == sizeof(vdl2_block_t), "block record layout");
 static_assert(sizeof(Vdl2StepRec) == sizeof(vdl2_step_t), "step record layout");
 static_assert(sizeof(Vdl2SyncRec) == sizeof(vdl2_sync_t), "sync record layout");
 static_assert(sizeof(Vdl2SymRec) == sizeof(vdl2_sym_t), "sym record layout");
+static_assert(sizeof(Vdl2FrameRec) == sizeof(vdl2_frame_t) && sizeof(vdl2_frame_t) == 2048, "frame record layout");
+static_assert(sizeof(Vdl2BlkStat) == sizeof(vdl2_blkstat_t), "block statistics layout");
 
 static thread_local std::string g_create_error;
 
@@ -68,6 +71,15 @@ struct vdl2gpu {
 	vdl2_stats_t st;
 	std::string err;
 	void *encode_fn;
+	/* block pipeline (vdl2_link.cu), allocated on first use */
+	Vdl2BlockRec *d_lblocks;
+	Vdl2FrameRec *d_frames;
+	Vdl2BlkStat *d_lstats;
+	uint8_t *d_lrows;
+	unsigned *d_nframes;
+	int lcap_blocks, lcap_frames;
+	cudaEvent_t lev0, lev1;
+	bool lev_valid, link_ready;
 };
 
 static int fail(vdl2gpu * h, const char *fmt, ...)
@@ -201,6 +213,13 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->row_bytes = h->row_samples * h->bytes_per_sample;
 	h->spc = 16 / h->bytes_per_sample;
 	h->ev_valid = false;
+	h->d_lblocks = NULL;
+	h->d_frames = NULL;
+	h->d_lstats = NULL;
+	h->d_lrows = NULL;
+	h->d_nframes = NULL;
+	h->lcap_blocks = h->lcap_frames = 0;
+	h->lev_valid = h->link_ready = false;
 	h->carry = 0;
 	h->rows_done = 0;
 	memset(&h->st, 0, sizeof h->st);
@@ -520,6 +539,15 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_tap_syncs);
 	cudaFree(h->d_tap_syms);
 	cudaFree(h->d_stage);
+	cudaFree(h->d_lblocks);
+	cudaFree(h->d_frames);
+	cudaFree(h->d_lstats);
+	cudaFree(h->d_lrows);
+	cudaFree(h->d_nframes);
+	if (h->link_ready) {
+		cudaEventDestroy(h->lev0);
+		cudaEventDestroy(h->lev1);
+	}
 	cudaEventDestroy(h->ev0);
 	cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
@@ -717,6 +745,154 @@ extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int
 	return 0;
 }
 
+/* ---- block pipeline ---- */
+static int link_reserve(vdl2gpu * h, int nblocks, int nframes, bool own_blocks)
+{
+	if (!h->link_ready) {
+		cudaError_t e = (cudaError_t) vdl2_link_upload_tables();
+		if (e != cudaSuccess)
+			return fail(h, "block pipeline: table upload failed: %s", cudaGetErrorString(e));
+		CK(h, cudaEventCreate(&h->lev0));
+		CK(h, cudaEventCreate(&h->lev1));
+		CK(h, cudaMalloc(&h->d_nframes, 16));
+		h->link_ready = true;
+	}
+	if (nblocks > h->lcap_blocks) {
+		cudaFree(h->d_lblocks);
+		cudaFree(h->d_lstats);
+		cudaFree(h->d_lrows);
+		h->d_lblocks = NULL;
+		h->d_lstats = NULL;
+		h->d_lrows = NULL;
+		const int cap = std::max(nblocks, 256);
+		if (own_blocks)
+			CK(h, cudaMalloc(&h->d_lblocks, sizeof(Vdl2BlockRec) * (size_t) cap));
+		CK(h, cudaMalloc(&h->d_lstats, sizeof(Vdl2BlkStat) * (size_t) cap));
+		CK(h, cudaMalloc(&h->d_lrows, (size_t) 2040 * cap));
+		h->lcap_blocks = cap;
+	} else if (own_blocks && !h->d_lblocks) {
+		CK(h, cudaMalloc(&h->d_lblocks, sizeof(Vdl2BlockRec) * (size_t) h->lcap_blocks));
+	}
+	if (nframes > h->lcap_frames) {
+		cudaFree(h->d_frames);
+		h->d_frames = NULL;
+		const int cap = std::max(nframes, 256);
+		CK(h, cudaMalloc(&h->d_frames, sizeof(Vdl2FrameRec) * (size_t) cap));
+		h->lcap_frames = cap;
+	}
+	return 0;
+}
+
+/* runs the kernel on nblocks device-resident blocks; copies the frames back, sorted by (block, length) */
+static int link_run(vdl2gpu * h, const Vdl2BlockRec * d_blocks, int nblocks, vdl2_frame_t * frames, int max_frames, int *n_frames,
+		    bool want_rows)
+{
+	*n_frames = 0;
+	if (nblocks <= 0)
+		return 0;
+	CK(h, cudaMemsetAsync(h->d_nframes, 0, 4, h->stream));
+	CK(h, cudaEventRecord(h->lev0, h->stream));
+	cudaError_t e = (cudaError_t) vdl2_link_launch(d_blocks, nblocks, h->d_frames, h->d_nframes, (unsigned)std::min(max_frames, h->lcap_frames),
+						       h->d_lstats, want_rows ? h->d_lrows : NULL, h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "block pipeline launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaEventRecord(h->lev1, h->stream));
+	h->lev_valid = true;
+	h->st.link_launches++;
+	unsigned nf = 0;
+	CK(h, cudaMemcpyAsync(&nf, h->d_nframes, 4, cudaMemcpyDeviceToHost, h->stream));
+	CK(h, cudaStreamSynchronize(h->stream));
+	if ((int)nf > max_frames || (int)nf > h->lcap_frames)
+		return fail(h, "block pipeline: %u frames, room for %d", nf, std::min(max_frames, h->lcap_frames));
+	if (nf) {
+		CK(h, cudaMemcpy(frames, h->d_frames, sizeof(Vdl2FrameRec) * (size_t) nf, cudaMemcpyDeviceToHost));
+		std::vector < int >idx(nf);
+		for (unsigned i = 0; i < nf; i++)
+			idx[i] = (int)i;
+		std::sort(idx.begin(), idx.end(),[&](int a, int b) {
+			  return frames[a].block != frames[b].block ? frames[a].block < frames[b].block : frames[a].len < frames[b].len;}
+		);
+		std::vector < vdl2_frame_t > tmp(frames, frames + nf);
+		for (unsigned i = 0; i < nf; i++)
+			frames[i] = tmp[idx[i]];
+	}
+	h->st.frames_out += nf;
+	*n_frames = (int)nf;
+	return 0;
+}
+
+extern "C" int vdl2_link_decode(vdl2gpu_t * h, const vdl2_block_t * blocks, int nblocks, vdl2_frame_t * frames, int max_frames, int *n_frames,
+				vdl2_blkstat_t * stats, uint8_t * rows_after)
+{
+	if (!h || !n_frames || (nblocks > 0 && (!blocks || !frames)))
+		return fail(h, "vdl2_link_decode: null argument");
+	*n_frames = 0;
+	if (nblocks <= 0)
+		return 0;
+	CK(h, cudaSetDevice(h->cfg.device));
+	if (link_reserve(h, nblocks, max_frames, true))
+		return 1;
+	CK(h, cudaMemcpyAsync(h->d_lblocks, blocks, sizeof(Vdl2BlockRec) * (size_t) nblocks, cudaMemcpyHostToDevice, h->stream));
+	if (link_run(h, h->d_lblocks, nblocks, frames, max_frames, n_frames, rows_after != NULL))
+		return 1;
+	if (stats)
+		CK(h, cudaMemcpy(stats, h->d_lstats, sizeof(Vdl2BlkStat) * (size_t) nblocks, cudaMemcpyDeviceToHost));
+	if (rows_after)
+		CK(h, cudaMemcpy(rows_after, h->d_lrows, (size_t) 2040 * nblocks, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int *n_frames, vdl2_block_t * blocks, int max_blocks,
+				 int *n_blocks)
+{
+	if (!h || !n_frames || !frames)
+		return fail(h, "vdl2_drain_frames: null argument");
+	*n_frames = 0;
+	if (n_blocks)
+		*n_blocks = 0;
+	CK(h, cudaSetDevice(h->cfg.device));
+	CK(h, cudaStreamSynchronize(h->stream));
+	unsigned cnt[8];
+	CK(h, cudaMemcpy(cnt, h->d_outq_count, sizeof cnt, cudaMemcpyDeviceToHost));
+	const unsigned n = std::min(cnt[0], h->outq_cap);
+	h->st.blocks_dropped += cnt[4];
+	if (cnt[4])
+		CK(h, cudaMemset(h->d_dropped, 0, 4));
+	if (n == 0)
+		return 0;
+	if (blocks && max_blocks < (int)n)
+		return fail(h, "vdl2_drain_frames: %u blocks pending, room for %d", n, max_blocks);
+	if (link_reserve(h, (int)n, max_frames, false))
+		return 1;
+	/* the block queue is in completion order; the kernel indexes it as it is, the host sorts afterwards */
+	if (link_run(h, h->d_outq, (int)n, frames, max_frames, n_frames, false))
+		return 1;
+	/* order of the blocks: oldest trigger first (the order drain_blocks returns); only the keys are needed */
+	std::vector < vdl2_block_t > q(n);
+	CK(h, cudaMemcpy(q.data(), h->d_outq, sizeof(Vdl2BlockRec) * (size_t) n, cudaMemcpyDeviceToHost));
+	CK(h, cudaMemset(h->d_outq_count, 0, 4));
+	std::vector < int >order(n), rank(n);
+	for (unsigned i = 0; i < n; i++)
+		order[i] = (int)i;
+	std::stable_sort(order.begin(), order.end(),[&](int a, int b) {
+			 return q[a].sync_dump != q[b].sync_dump ? q[a].sync_dump < q[b].sync_dump : q[a].chn < q[b].chn;}
+	);
+	for (unsigned i = 0; i < n; i++)
+		rank[order[i]] = (int)i;
+	for (int i = 0; i < *n_frames; i++)
+		frames[i].block = rank[frames[i].block];
+	std::stable_sort(frames, frames + *n_frames,[](const vdl2_frame_t & a, const vdl2_frame_t & b) {
+			 return a.block != b.block ? a.block < b.block : a.len < b.len;}
+	);
+	if (blocks)
+		for (unsigned i = 0; i < n; i++)
+			blocks[i] = q[order[i]];
+	h->st.blocks_out += n;
+	if (n_blocks)
+		*n_blocks = (int)n;
+	return 0;
+}
+
 template < class T > static int read_tap(vdl2gpu * h, int ch, T * d_base, unsigned cap, size_t off_count, T * out, size_t max,
 					  size_t *n_out)
 {
@@ -777,6 +953,12 @@ extern "C" int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st)
 		float ms = 0;
 		CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 		h->st.last_kernel_ms = ms;
+	}
+	if (h->lev_valid) {
+		CK(h, cudaEventSynchronize(h->lev1));
+		float ms = 0;
+		CK(h, cudaEventElapsedTime(&ms, h->lev0, h->lev1));
+		h->st.last_link_ms = ms;
 	}
 	*st = h->st;
 	return 0;

@@ -12,7 +12,7 @@
 #endif		/* TMA boxes (32 rows x 128 B) in flight per warp */
 
 #ifndef VDL2_D8_NST
-#define VDL2_D8_NST 4		/* per-dump TMA boxes (32 rows x 64 B) in flight per warp, integer mixer */
+#define VDL2_D8_NST 3		/* per-dump TMA boxes (32 rows x 64 B) in flight per warp, integer mixer */
 #endif
 
 #ifdef __cplusplus
