@@ -279,6 +279,45 @@ def run_ours(args, rank, local_rank, world):
                "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep}
         del hx
 
+    # ---- block pipeline behind the demodulator: the blocks of one step through
+    #      vdl2_link_kernel (RS + HDLC + FCS), next to the reference's blk_thread path on one host core
+    link = None
+    if rank == 0:
+        try:
+            step()
+            g.sync()
+            blks = g.drain_blocks()
+            lms, nfr = [], 0
+            for _ in range(4):
+                fr, _st, _ = g.link_decode(blks, want_rows=False)
+                lms.append(g.stats()["last_link_ms"])
+                nfr = len(fr)
+            lk = sum(lms[1:]) / len(lms[1:])
+            step()
+            g.sync()
+            t0 = time.perf_counter()
+            fr2, _b2 = g.drain_frames()
+            fused_s = time.perf_counter() - t0
+            lbytes = len(blks) * 2080 + nfr * 2048
+            link = {"kernel": "vdl2_link_kernel", "blocks": int(len(blks)), "frames": int(nfr), "kernel_ms": lk,
+                    "blocks_per_s": len(blks) / (lk * 1e-3) if lk > 0 else None,
+                    "algorithmic_bytes": lbytes, "achieved_gbs": lbytes / (lk * 1e-3) / 1e9 if lk > 0 else None,
+                    "bound": "lsu (shared-memory table look-ups; 4 KB of HBM traffic per block)",
+                    "drain_frames_ms_host": fused_s * 1e3, "frames_fused": int(len(fr2))}
+            if not args.no_cpu:
+                from oracle import pyoracle
+                kind = "ref" if pyoracle.link_available("ref") else "port"
+                sub = blks[:min(len(blks), 2048)]
+                t1 = pyoracle.link_time(kind, sub, 1)
+                reps = max(1, min(50, int(3.0 / max(t1, 1e-4))))
+                tt = pyoracle.link_time(kind, sub, reps)
+                link["cpu_baseline"] = {"value": len(sub) * reps / tt, "unit": "blocks/s", "cores": 1,
+                                        "kind": "reference" if kind == "ref" else "port",
+                                        "sample": f"{reps} passes over {len(sub)} blocks of the step through the reference's blk_thread "
+                                                  f"(vdlm2.c + rs.c + crc.c, single consumer thread as in the reference)"}
+        except Exception as exc:  # the headline must not depend on the optional row
+            link = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,6 +361,7 @@ def run_ours(args, rank, local_rank, world):
                    "bursts_per_step_per_gpu": nbursts, "blocks_decoded_per_step": blocks_timed // max(1, args.steps) if blocks_timed else blocks_seen,
                    "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "link": link,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,6 +16,7 @@ from vdlm2dec_b200 import synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_cpu")
 GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu")
+LINK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu_link")   # shim also replaces vdlm2.o + rs.o (row f1)
 ALL = ("-G", "-E", "-U")  # print ground, empty and undecoded frames too
 needs_bins = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(GPU_BIN)), reason="drop-in binaries not built")
 
@@ -130,3 +131,21 @@ def test_dropin_acars_json_identical(tmp_path):
     want = _expected_blocks(cap, [-50_000, -175_000])
     assert len(jb) == want and len(set(ja) & set(jb)) >= want // 2  # see the race note above
     assert '"text":"HELLO VDL2 NUMBER 0' in "".join(ja)
+
+
+@pytest.mark.gpu
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(LINK_BIN), reason="drop-in binary for row f1 not built")
+def test_dropin_block_pipeline_on_device(tmp_path):
+    """Row f1: the shim built with -DVDL2_SHIM_LINK also replaces vdlm2.o and rs.o -- the blocks go through rs(),
+    HDLC un-stuffing and the FCS check on the device and out() is called with the frames.  Same text and JSON as
+    the binary that keeps the reference's blk_thread."""
+    cap, nb = _capture(tmp_path, [-50_000, -175_000], nblk=40, seed=7, acars=True)
+    freqs = ["136.975", "136.850"]
+    a = _run(GPU_BIN, cap, freqs, extra=("-J",))[0]
+    b = _run(LINK_BIN, cap, freqs, extra=("-J",))[0]
+    ja = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in a.splitlines() if l.startswith("{"))
+    jb = sorted(re.sub(r'"timestamp":[0-9.]+', '"timestamp":0', l) for l in b.splitlines() if l.startswith("{"))
+    assert len(jb) == _expected_blocks(cap, [-50_000, -175_000]) and ja == jb
+    cap2, _ = _capture(tmp_path, [-50_000], seed=5)
+    assert _messages(_run(GPU_BIN, cap2, ["136.975"], extra=ALL)[0]) == _messages(_run(LINK_BIN, cap2, ["136.975"], extra=ALL)[0])

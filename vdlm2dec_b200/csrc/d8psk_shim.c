@@ -17,6 +17,12 @@
  * drains the completed blocks and passes each to decodeVdlm2() through the channel_t of
  * the channel it belongs to (ownership of ch->blk as in vdlm2.c:189-205).
  * CUDA failure: message on stderr + exit(1) (the reference's only error convention).
+ *
+ * -DVDL2_SHIM_LINK (the next row of the scope table): the object ALSO takes the
+ * place of vdlm2.o and rs.o.  It then exports initVdlm2 / decodeVdlm2 / stopVdlm2 (vdlm2.h:116-118) itself,
+ * no blk_thread is started, and instead of handing blocks to decodeVdlm2() the leader drains FRAMES -- the
+ * blocks went through rs(), HDLC un-stuffing and the FCS check on the device (vdl2_drain_frames) -- and calls
+ * out(blk, hdata, l) (vdlm2.h:134) exactly where check_frame() would (vdlm2.c:60).
  */
 #define _GNU_SOURCE
 #include <stdio.h>
@@ -88,6 +94,49 @@ static void gpu_open(void)
 	atexit(quiesce);
 }
 
+#ifdef VDL2_SHIM_LINK
+int initVdlm2(channel_t * ch)
+{				/* vdlm2.c:163-180 without the consumer thread: frames are produced on the device */
+	ch->state = WSYNC;
+	ch->blk = calloc(sizeof(msgblk_t), 1);
+	ch->blk->chn = ch->chn;
+	ch->blk->Fr = ch->Fr;
+	return 0;
+}
+
+void decodeVdlm2(channel_t * ch)
+{				/* never called by this object; kept for link compatibility (vdlm2.h:118) */
+	(void)ch;
+}
+
+void stopVdlm2(void)
+{				/* main.c:108,244: nothing is queued on the host */
+}
+
+static void gpu_block(void)
+{
+	static vdl2_frame_t fr[1024];
+	static vdl2_block_t bl[1024];
+	int nf = 0, nb = 0;
+	pthread_mutex_lock(&g_busy);
+	if (vdl2_process_host(g_gpu, Cbuff, RTLINBUFSZ / 2, 0))
+		die("vdl2_process_host");
+	if (vdl2_drain_frames(g_gpu, fr, 1024, &nf, bl, 1024, &nb))
+		die("vdl2_drain_frames");
+	for (int i = 0; i < nf; i++) {
+		msgblk_t blk;	/* what check_frame() passes on (vdlm2.c:60): only the header fields are read downstream */
+		memset(&blk, 0, sizeof blk);
+		blk.chn = fr[i].chn;
+		blk.Fr = fr[i].Fr;
+		blk.ppm = fr[i].ppm;
+		blk.nbrow = bl[fr[i].block].nbrow;
+		blk.nlbyte = bl[fr[i].block].nlbyte;
+		gettimeofday(&blk.tv, NULL);	/* d8psk.c:295 (wall clock in the reference too) */
+		out(&blk, fr[i].hdata, fr[i].len);
+	}
+	pthread_mutex_unlock(&g_busy);
+}
+#else
 static void gpu_block(void)
 {
 	static vdl2_block_t out[1024];
@@ -115,6 +164,7 @@ static void gpu_block(void)
 	}
 	pthread_mutex_unlock(&g_busy);
 }
+#endif
 
 void *rcv_thread(void *arg)
 {
