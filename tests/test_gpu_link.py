@@ -84,3 +84,36 @@ def test_drain_frames_fused_with_the_demodulator():
     assert st["link_launches"] == 1 and st["frames_out"] == len(frames)
     f2, b2 = b.drain_frames()
     assert len(f2) == 0 and len(b2) == 0
+
+
+def test_link_full_size_round_trip(gpu):
+    """Size-independent property at bench scale: 16384 bursts, transmitted frame -> RS-protected rows -> up to the
+    code's capacity of byte errors per row -> the kernel must hand back exactly the transmitted frame for every block
+    (and agree with the oracle on everything else)."""
+    from vdlm2dec_b200 import synth
+    from tests.link_util import block_from_burst
+    rng = np.random.default_rng(123)
+    base, want = [], []
+    for i in range(256):
+        payload = synth.random_payload(rng, int(rng.integers(14, 1200)))
+        b = synth.Burst(synth.hdlc_bits(payload))
+        blk = block_from_burst(b, chn=i % 8, sync_dump=i)
+        d = blk["data"]
+        for r in range(b.nbrow):
+            last = r == b.nbrow - 1
+            cap = 3 if not last or b.nlbyte > 67 else (2 if b.nlbyte > 30 else (1 if b.nlbyte > 2 else 0))
+            width = b.nlbyte if last else 249
+            for c in rng.choice(width, size=min(cap, width), replace=False):
+                d[r, c] ^= np.uint8(rng.integers(1, 256))
+        blk["data"] = d
+        base.append(blk)
+        fcs = synth.fcs16(payload)
+        want.append(bytes([0x7E]) + payload + bytes([fcs & 0xFF, fcs >> 8, 0x7E]))
+    blocks = np.tile(np.array(base), 64)
+    blocks["sync_dump"] = np.arange(len(blocks))
+    f, s, _ = gpu.link_decode(blocks, want_rows=False)
+    assert len(f) == len(blocks) == 16384 and np.array_equal(f["block"], np.arange(len(blocks)))
+    assert (s["nframes"] == 1).all() and (s["rs"] >= 0).all()
+    for i in range(0, len(f), 97):
+        assert bytes(f[i]["hdata"][:f[i]["len"]]) == want[i % 256]
+    assert np.array_equal(f["len"], np.array([len(w) for w in want] * 64))
