@@ -180,8 +180,8 @@ typedef struct {
 int vdl2_link_decode(vdl2gpu_t * h, const vdl2_block_t * blocks, int nblocks, vdl2_frame_t * frames, int max_frames, int *n_frames,
 		     vdl2_blkstat_t * stats, uint8_t * rows_after);
 /* like vdl2_drain_blocks, but the completed blocks go through the block pipeline ON THE DEVICE first (no
-   round trip): returns the frames and, if blocks != NULL, the blocks themselves (oldest trigger first;
-   frame.block indexes them) */
+   round trip): returns the frames (oldest trigger first, then channel, then position) and, if blocks != NULL,
+   the blocks themselves in the same order (frame.block indexes them; -1 when the blocks were not asked for) */
 int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int *n_frames, vdl2_block_t * blocks, int max_blocks,
 		      int *n_blocks);
 

@@ -116,12 +116,11 @@ void stopVdlm2(void)
 static void gpu_block(void)
 {
 	static vdl2_frame_t fr[1024];
-	static vdl2_block_t bl[1024];
 	int nf = 0, nb = 0;
 	pthread_mutex_lock(&g_busy);
 	if (vdl2_process_host(g_gpu, Cbuff, RTLINBUFSZ / 2, 0))
 		die("vdl2_process_host");
-	if (vdl2_drain_frames(g_gpu, fr, 1024, &nf, bl, 1024, &nb))
+	if (vdl2_drain_frames(g_gpu, fr, 1024, &nf, NULL, 0, &nb))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
 		die("vdl2_drain_frames");
 	for (int i = 0; i < nf; i++) {
 		msgblk_t blk;	/* what check_frame() passes on (vdlm2.c:60): only the header fields are read downstream */
@@ -129,8 +128,6 @@ static void gpu_block(void)
 		blk.chn = fr[i].chn;
 		blk.Fr = fr[i].Fr;
 		blk.ppm = fr[i].ppm;
-		blk.nbrow = bl[fr[i].block].nbrow;
-		blk.nlbyte = bl[fr[i].block].nlbyte;
 		gettimeofday(&blk.tv, NULL);	/* d8psk.c:295 (wall clock in the reference too) */
 		out(&blk, fr[i].hdata, fr[i].len);
 	}

@@ -867,26 +867,31 @@ extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_f
 	/* the block queue is in completion order; the kernel indexes it as it is, the host sorts afterwards */
 	if (link_run(h, h->d_outq, (int)n, frames, max_frames, n_frames, false))
 		return 1;
-	/* order of the blocks: oldest trigger first (the order drain_blocks returns); only the keys are needed */
-	std::vector < vdl2_block_t > q(n);
-	CK(h, cudaMemcpy(q.data(), h->d_outq, sizeof(Vdl2BlockRec) * (size_t) n, cudaMemcpyDeviceToHost));
-	CK(h, cudaMemset(h->d_outq_count, 0, 4));
-	std::vector < int >order(n), rank(n);
-	for (unsigned i = 0; i < n; i++)
-		order[i] = (int)i;
-	std::stable_sort(order.begin(), order.end(),[&](int a, int b) {
-			 return q[a].sync_dump != q[b].sync_dump ? q[a].sync_dump < q[b].sync_dump : q[a].chn < q[b].chn;}
-	);
-	for (unsigned i = 0; i < n; i++)
-		rank[order[i]] = (int)i;
-	for (int i = 0; i < *n_frames; i++)
-		frames[i].block = rank[frames[i].block];
-	std::stable_sort(frames, frames + *n_frames,[](const vdl2_frame_t & a, const vdl2_frame_t & b) {
-			 return a.block != b.block ? a.block < b.block : a.len < b.len;}
-	);
-	if (blocks)
+	CK(h, cudaMemsetAsync(h->d_outq_count, 0, 4, h->stream));
+	if (blocks) {
+		/* order of the blocks: oldest trigger first (the order drain_blocks returns); frame.block follows it */
+		std::vector < vdl2_block_t > q(n);
+		CK(h, cudaMemcpy(q.data(), h->d_outq, sizeof(Vdl2BlockRec) * (size_t) n, cudaMemcpyDeviceToHost));
+		std::vector < int >order(n), rank(n);
+		for (unsigned i = 0; i < n; i++)
+			order[i] = (int)i;
+		std::stable_sort(order.begin(), order.end(),[&](int a, int b) {
+				 return q[a].sync_dump != q[b].sync_dump ? q[a].sync_dump < q[b].sync_dump : q[a].chn < q[b].chn;}
+		);
+		for (unsigned i = 0; i < n; i++)
+			rank[order[i]] = (int)i;
+		for (int i = 0; i < *n_frames; i++)
+			frames[i].block = rank[frames[i].block];
 		for (unsigned i = 0; i < n; i++)
 			blocks[i] = q[order[i]];
+	} else {
+		for (int i = 0; i < *n_frames; i++)
+			frames[i].block = -1;	/* the blocks were not asked for; chn / Fr / ppm / sync_dump travel in the frame */
+	}
+	/* same order either way: by trigger time, then channel, then position inside the block */
+	std::stable_sort(frames, frames + *n_frames,[](const vdl2_frame_t & a, const vdl2_frame_t & b) {
+			 return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : (a.chn != b.chn ? a.chn < b.chn : a.len < b.len);}
+	);
 	h->st.blocks_out += n;
 	if (n_blocks)
 		*n_blocks = (int)n;
