@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -75,9 +75,16 @@ class ClockSampler:
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.2)
         self.proc.terminate()
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        if not rows:  # nvidia-smi was too slow to start: one direct query right after the timed region
+            try:
+                q = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+                rows = [[x.strip() for x in q[0].split(",")]] if q else []
+            except Exception:
+                rows = []
         sm, mx, reasons = [], None, set()
         for r in rows:
             try:
@@ -181,7 +188,7 @@ def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from vdlm2dec_b200.api import Vdl2Gpu
+    from vdlm2dec_b200.api import OPT_OVERLAP, Vdl2Gpu
     from vdlm2dec_b200.synth_torch import make_device_workload
 
     if not torch.cuda.is_available():
@@ -208,7 +215,9 @@ def run_ours(args, rank, local_rank, world):
         chans = [(c + rank * nch, 136_975_000, fos[c]) for c in range(nch)]
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
-    g = Vdl2Gpu(chans, ch_per_stream=cps, device=local_rank, max_samples=ns,
+    # OPT_OVERLAP: back-to-back launches may overlap on the device (programmatic dependent launch); the library then
+    # records no per-launch events, the bench brackets with its own
+    g = Vdl2Gpu(chans, ch_per_stream=cps, device=local_rank, max_samples=ns, taps=OPT_OVERLAP,
                 max_blocks=(args.steps + 4) * max(nbursts, 64) * cps + 4096)
     stream = torch.cuda.ExternalStream(g.cuda_stream, device=dev)
 
@@ -224,7 +233,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- timed region: K launches, CUDA events on the launching stream, barrier + sync both sides
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    for _ in range(40):  # wait until nvidia-smi delivers (its start-up can take a second on a fresh box)
+        if sampler.rows:
+            break
+        time.sleep(0.05)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = g.stats()["kernel_launches"]
@@ -242,9 +254,12 @@ def run_ours(args, rank, local_rank, world):
     blocks_timed = len(g.drain_blocks())
     # per-launch kernel time (events recorded by the library around the kernel on its stream)
     for _ in range(3):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
         step()
+        k1.record(stream)
         g.sync()
-        kernel_ms.append(g.stats()["last_kernel_ms"])
+        kernel_ms.append(k0.elapsed_time(k1))
         g.drain_blocks()
     kms = sum(kernel_ms) / len(kernel_ms)
 
@@ -359,7 +374,8 @@ def run_ours(args, rank, local_rank, world):
                                f"config 4 = the same per GPU at N=8)", "channels_per_gpu": nch, "samples_per_channel": ns,
                    "bytes_per_step_per_gpu": alg_bytes, "l2": "input per step (8 GiB at defaults) >> 126 MB L2; no flush needed",
                    "bursts_per_step_per_gpu": nbursts, "blocks_decoded_per_step": blocks_timed // max(1, args.steps) if blocks_timed else blocks_seen,
-                   "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1)},
+                   "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1),
+                   "launch_mode": "back-to-back launches with programmatic dependent launch (tails overlap)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "link": link,
     }

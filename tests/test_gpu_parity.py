@@ -10,7 +10,7 @@ import pytest
 from oracle.pyoracle import Oracle
 from tests.parity_util import compare_channel, make_channels, run_oracle
 from vdlm2dec_b200 import synth
-from vdlm2dec_b200.api import OPT_EXACT_IDLE, OPT_FLOAT_MIX, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
+from vdlm2dec_b200.api import OPT_EXACT_IDLE, OPT_FLOAT_MIX, OPT_OVERLAP, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
 
 pytestmark = pytest.mark.gpu
 ALL_TAPS = TAP_DUMPS | TAP_STEPS | TAP_SYNCS | TAP_SYMS  # TAP_STEPS implies the exact fit at every idle step
@@ -170,6 +170,33 @@ def test_device_resident_zero_copy_equals_host_path():
     bb = b.drain_blocks()
     assert len(ba) == len(bb) > 0 and ba.tobytes() == bb.tobytes()
     _check_all(b, specs, iq, "cu8", blocks=bb, taps=False, ndump_limit=n // 2000 * 84)
+
+
+def test_overlapping_launches_equal_one_launch():
+    """OPT_OVERLAP: launches are issued back to back without host synchronisation and may overlap on the device
+    (programmatic dependent launch; the per-channel order is kept by the kernel's progress flags, the work counters
+    rotate, scratch slots are taken per SM).  Chunked launches of 32..96 rows must give exactly the blocks of
+    one launch over the whole buffer."""
+    import torch
+    nch, n = 24, 1_984_000
+    specs, iq = make_channels(nch, n, seed=16, period=150_000)
+    chans = [(c, 136_975_000, specs[c].Fo) for c in range(nch)]
+    t = torch.from_numpy(iq).cuda()
+    a = Vdl2Gpu(chans, max_samples=n)
+    a.process_device(t.data_ptr(), n, t.stride(0))
+    a.sync()
+    ba = a.drain_blocks()
+    b = Vdl2Gpu(chans, taps=OPT_OVERLAP, max_samples=n)
+    pos, k = 0, 0
+    while pos < n:
+        m = min(n - pos, 2000 * (32, 64, 96)[k % 3])
+        b.process_device(t.data_ptr() + 2 * pos, m, t.stride(0))      # 2 bytes per cu8 IQ sample; a multiple of 16
+        pos += m
+        k += 1
+    b.sync()
+    bb = b.drain_blocks()
+    assert k >= 12 and len(ba) == len(bb) >= nch and ba.tobytes() == bb.tobytes()
+    assert b.stats()["kernel_launches"] == k
 
 
 @pytest.mark.parametrize("nlbyte_class", ["le2", "le30", "le67", "gt67", "zero", "rows8"])

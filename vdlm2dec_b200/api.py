@@ -24,6 +24,7 @@ FMT_DTYPE = {"cu8": np.uint8, "cs8": np.int8, "cs16": np.int16, "cf32": np.float
 FMT_BYTES = {"cu8": 2, "cs8": 2, "cs16": 4, "cf32": 8, "f32real": 4}
 TAP_DUMPS, TAP_STEPS, TAP_SYNCS, TAP_SYMS = 1, 2, 4, 8
 OPT_EXACT_IDLE = 0x100
+OPT_OVERLAP = 0x400  # consecutive launches may overlap (PDL); no per-launch kernel time
 OPT_FLOAT_MIX = 0x200  # cu8/cs8: generic fp32 mixer instead of the integer dot-product mixer (A/B, parity tests)
 
 STEP_DT = np.dtype([("dump", "<i8"), ("P", "<f4"), ("err", "<f4"), ("fr", "<f4"), ("pad", "<i4")])

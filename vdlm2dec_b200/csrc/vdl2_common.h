@@ -96,8 +96,14 @@ struct Vdl2KParams {
 	int sched_slot;		/* which c_tab.sched_slots[] row: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte
 				   chunks, then the chunk in which the dump ends after sample E; w0 = index of the dump's
 				   first chunk in the (extended) oscillator table */
-	unsigned *ticket;	/* work counter */
-	int *progress;		/* [nch]: tiles completed in this launch */
+	unsigned *ticket;	/* work counters [0..2], rotating per launch (ticket_sel); [3] launches completed; [4] block queue count;
+				   [5..7] CTAs exited per counter slot; [8] dropped; [12..15] statistics */
+	int ticket_sel;
+	int launch_seq;		/* launches of this handle before this one */
+	int tile_base;		/* tiles per channel completed by earlier launches */
+	int *progress;		/* [nch]: tiles completed since create */
+	unsigned *slotmask;	/* [nsmid]: scratch slots in use per SM */
+	int slots_per_sm;
 	uint8_t *curblk;	/* [nch][2048] block under construction */
 	float2 *scratch;	/* [grid][VDL2_HIST + VDL2_TILE_DUMPS]: decimated stream of the tile a warp works on */
 	Vdl2BlockRec *outq;

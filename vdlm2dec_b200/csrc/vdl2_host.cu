@@ -53,7 +53,12 @@ struct vdl2gpu {
 	int dp4a;		/* 1: cu8/cs8 at a rate whose dumps are 23/24 samples -> integer dot-product mixer */
 	int sched_slot;
 	unsigned *d_ticket;
+	unsigned *d_slotmask;
+	unsigned nsmid;
 	int *d_progress;
+	int tiles_done;		/* per channel, since create */
+	unsigned launch_seq;
+	bool overlap;		/* VDL2_OPT_OVERLAP: no per-launch events, consecutive launches may overlap */
 	uint8_t *d_curblk;
 	float2 *d_scratch;
 	Vdl2BlockRec *d_outq;
@@ -475,10 +480,23 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->d_outq_count = h->d_ticket + 4;
 	h->d_dropped = h->d_ticket + 8;
 	CK(h, cudaMalloc(&h->d_progress, sizeof(int) * nch));
+	CK(h, cudaMemset(h->d_progress, 0, sizeof(int) * nch));
+	h->tiles_done = 0;
+	h->launch_seq = 0;
+	h->overlap = (cfg->taps & VDL2_OPT_OVERLAP) != 0;
+	h->nsmid = 0;
+	if (vdl2_kernel_nsmid(h->d_ticket + 15, &h->nsmid) || h->nsmid == 0 || h->nsmid > 1024)
+		return fail(h, "vdl2_create: cannot query the SM id range");
+	CK(h, cudaMemset(h->d_ticket + 15, 0, 4));
+	CK(h, cudaMalloc(&h->d_slotmask, sizeof(unsigned) * h->nsmid));
+	CK(h, cudaMemset(h->d_slotmask, 0, sizeof(unsigned) * h->nsmid));
 	CK(h, cudaMalloc(&h->d_curblk, (size_t) nch * 2048));
 	CK(h, cudaMemset(h->d_curblk, 0, (size_t) nch * 2048));
-	CK(h, cudaMalloc(&h->d_scratch, sizeof(float2) * (size_t) h->grid * (VDL2_HIST + VDL2_TILE_DUMPS)));
-	CK(h, cudaMemset(h->d_scratch, 0, sizeof(float2) * (size_t) h->grid * (VDL2_HIST + VDL2_TILE_DUMPS)));
+	{	/* one scratch slot per (SM id, resident CTA); SM ids are not contiguous on parts with disabled SMs */
+		const size_t nslots = (size_t) h->nsmid * h->ctas_per_sm;
+		CK(h, cudaMalloc(&h->d_scratch, sizeof(float2) * nslots * (VDL2_HIST + VDL2_TILE_DUMPS)));
+		CK(h, cudaMemset(h->d_scratch, 0, sizeof(float2) * nslots * (VDL2_HIST + VDL2_TILE_DUMPS)));
+	}
 	h->outq_cap = cfg->max_blocks > 0 ? (unsigned)cfg->max_blocks : (unsigned)std::max(4096, nch * 8);
 	CK(h, cudaMalloc(&h->d_outq, sizeof(Vdl2BlockRec) * (size_t) h->outq_cap));
 
@@ -531,6 +549,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_w8);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
+	cudaFree(h->d_slotmask);
 	cudaFree(h->d_curblk);
 	cudaFree(h->d_scratch);
 	cudaFree(h->d_outq);
@@ -605,7 +624,12 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.w8 = h->d_w8;
 	kp.sched_slot = h->sched_slot;
 	kp.ticket = h->d_ticket;
+	kp.ticket_sel = (int)(h->launch_seq % 3u);
+	kp.launch_seq = (int)h->launch_seq;
+	kp.tile_base = h->tiles_done;
 	kp.progress = h->d_progress;
+	kp.slotmask = h->d_slotmask;
+	kp.slots_per_sm = h->ctas_per_sm;
 	kp.curblk = h->d_curblk;
 	kp.scratch = h->d_scratch;
 	kp.outq = h->d_outq;
@@ -625,7 +649,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.cap_syncs = h->cap_syncs;
 	kp.cap_syms = h->cap_syms;
 
-	CK(h, cudaMemsetAsync(h->d_ticket, 0, 4, h->stream));
+
 	if (getenv("VDL2_PRE_STATS")) {	/* debug: outcome counters of the speculative pass A of the previous launch */
 		unsigned c[4];
 		cudaStreamSynchronize(h->stream);
@@ -633,15 +657,20 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 		fprintf(stderr, "vdl2gpu: prepass used %u wasted %u idle-without %u burst-start %u\n", c[0], c[1], c[2], c[3]);
 		cudaMemset(h->d_ticket + 12, 0, sizeof c);
 	}
-	CK(h, cudaMemsetAsync(h->d_progress, 0, sizeof(int) * h->cfg.nch, h->stream));
+
 	const long long items = (long long)kp.ntiles * kp.nch;
 	const int grid = (int)std::min < long long >(items, h->grid);
-	CK(h, cudaEventRecord(h->ev0, h->stream));
+	if (!h->overlap)	/* an event between two kernels would serialise them */
+		CK(h, cudaEventRecord(h->ev0, h->stream));
 	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, h->dp4a, &tmap, &kp, grid, h->smem, h->stream);
 	if (e != cudaSuccess)
 		return fail(h, "kernel launch failed: %s", cudaGetErrorString(e));
-	CK(h, cudaEventRecord(h->ev1, h->stream));
-	h->ev_valid = true;
+	if (!h->overlap) {
+		CK(h, cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = true;
+	}
+	h->launch_seq++;
+	h->tiles_done += kp.ntiles;
 	h->st.kernel_launches++;
 	h->st.grid = grid;
 	h->rows_done += nrows;

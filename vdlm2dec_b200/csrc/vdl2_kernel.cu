@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <stddef.h>
 #include "vdl2_demod.cuh"
 #include "vdl2_kernel.h"
@@ -482,7 +483,44 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	float *hv = reinterpret_cast < float *>(smem + STAGES_BYTES + 64);
 	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
 	/* the decimated stream of the tile lives in global memory (L2): sd[0..15] history, sd[16 + i] dump i */
-	float2 *sd = kp.scratch + (size_t) blockIdx.x * (VDL2_HIST + VDL2_TILE_DUMPS);
+	/* Scratch slot: one per CTA that can be resident on this SM.  Consecutive launches may overlap (programmatic
+	   dependent launch: the next launch's CTAs move in while this one's tail drains), so the slot is taken from a
+	   per-SM bit mask instead of blockIdx. */
+	unsigned smid;
+	asm volatile ("mov.u32 %0, %%smid;":"=r" (smid));
+	unsigned slotbit = 0;
+	if (lane == 0) {
+		unsigned *m = kp.slotmask + smid;
+		const unsigned all = kp.slots_per_sm >= 32 ? 0xffffffffu : ((1u << kp.slots_per_sm) - 1u);
+		for (;;) {
+			const unsigned freeb = ~(*(volatile unsigned *)m) & all;
+			if (!freeb) {
+				__nanosleep(100);
+				continue;
+			}
+			const unsigned bit = freeb & (0u - freeb);
+			if (!(atomicOr(m, bit) & bit)) {
+				slotbit = bit;
+				break;
+			}
+		}
+	}
+	slotbit = __shfl_sync(0xffffffffu, slotbit, 0);
+	float2 *sd = kp.scratch + ((size_t) smid * kp.slots_per_sm + (__ffs(slotbit) - 1)) * (VDL2_HIST + VDL2_TILE_DUMPS);
+	/* At most two launches are active at a time: this one waits until the launch before the previous one has
+	   completed (ticket[3] counts completed launches; they complete in order because every launch continues every
+	   channel's chain).  Work counters rotate over three slots: this launch uses ticket[ticket_sel] and clears the one
+	   the NEXT launch will use (last used two launches ago).  Only then may the next launch start. */
+	if (lane == 0) {
+		while ((int)(*(volatile unsigned *)(kp.ticket + 3)) < kp.launch_seq - 1)
+			__nanosleep(500);
+		if (blockIdx.x == 0) {
+			kp.ticket[(kp.ticket_sel + 1) % 3] = 0u;
+			__threadfence();
+		}
+	}
+	__syncwarp();
+	asm volatile ("griddepcontrol.launch_dependents;":::"memory");
 	/* phase 2 scratch lives in the TMA stages, which are idle while a tile is demodulated */
 	IdleScratch scr;
 	scr.pht = reinterpret_cast < float *>(stage0);
@@ -516,7 +554,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	for (;;) {
 		int item = 0;
 		if (lane == 0)
-			item = (int)atomicAdd(kp.ticket, 1u);
+			item = (int)atomicAdd(kp.ticket + kp.ticket_sel, 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (item >= nitems)
 			break;
@@ -657,7 +695,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				/* wait for the previous tile of this channel, load its state */
 				if (lane == 0) {
 					const volatile int *pr = kp.progress + ch;
-					while (*pr < tile)
+					while (*pr < kp.tile_base + tile)	/* tiles completed since create: launches may overlap */
 						__nanosleep(200);
 				}
 				__syncwarp();
@@ -748,9 +786,26 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		__threadfence();
 		__syncwarp();
 		if (lane == 0)
-			atomicExch(kp.progress + ch, tile + 1);
+			atomicExch(kp.progress + ch, kp.tile_base + tile + 1);
 		__syncwarp();
 	}
+	if (lane == 0) {
+		atomicAnd(kp.slotmask + smid, ~slotbit);
+		/* the last CTA out marks the launch as completed */
+		if (atomicAdd(kp.ticket + 5 + kp.ticket_sel, 1u) == gridDim.x - 1) {
+			kp.ticket[5 + kp.ticket_sel] = 0u;
+			__threadfence();
+			atomicAdd(kp.ticket + 3, 1u);
+		}
+	}
+}
+
+/* highest SM id + 1 (ids are not contiguous on parts with disabled SMs): sizes the scratch and the slot masks */
+__global__ void vdl2_nsmid_kernel(unsigned *out)
+{
+	unsigned n;
+	asm volatile ("mov.u32 %0, %%nsmid;":"=r" (n));
+	*out = n;
 }
 
 }				/* namespace vdl2 */
@@ -769,8 +824,18 @@ template < int FMT, bool DP, bool TAPS > static cudaError_t launch_fmt2(const CU
 	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess)
 		return e;
-	vdl2::vdl2_frontend_kernel < FMT, DP, TAPS > <<<grid, 32, smem, st >>> (tmap, kp);
-	return cudaGetLastError();
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3(32);
+	cfg.dynamicSmemBytes = (size_t) smem;
+	cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;	/* the next launch may start while this one's tail drains */
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, tmap, kp);
 }
 
 template < int FMT, bool DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
@@ -835,6 +900,13 @@ extern "C" int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_
 	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL, false > (smem, ctas_per_sm);
 	}
 	return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int vdl2_kernel_nsmid(unsigned *d_scratch_word, unsigned *out)
+{
+	vdl2::vdl2_nsmid_kernel <<< 1, 1 >>> (d_scratch_word);
+	cudaError_t e = cudaMemcpy(out, d_scratch_word, 4, cudaMemcpyDeviceToHost);
+	return (int)e;
 }
 
 extern "C" int vdl2_kernel_upload_tables(const Vdl2Tables * t)
