@@ -91,6 +91,8 @@ struct Vdl2KParams {
 	Vdl2ChanState *state;
 	const float4 *wtab;	/* [nch][nco_pairs]: (re[n], re[n+1], im[n], im[n+1]) */
 	const float4 *dcorr;	/* [nch][84]: per dump (1/nf, 1/nf, -cre/nf, -cim/nf), see dump_close */
+	const float *soft;	/* [3][260]: copy of Vdl2Tables.soft in global memory (per-lane indexed look-ups), may be NULL */
+	const unsigned *scr;	/* [VDL2_SCR_WORDS]: copy of Vdl2Tables.scr, same reason (valid when soft is) */
 	const uint4 *w8;	/* integer mixer only, [nch][VDL2_W8_ENTRIES]: (digit 2, digit 1, digit 0, 0) words of signed bytes
 				   (wr[n], wi[n], wr[n+1], wi[n+1]); sched word = (first sample << 16) | (last entry << 8) | first entry */
 	int sched_slot;		/* which c_tab.sched_slots[] row: per dump of a row, (w0 << 16) | (E << 8) | np: np whole 16-byte

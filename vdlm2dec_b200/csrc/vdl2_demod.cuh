@@ -73,6 +73,7 @@ VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
 VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
 VQ float fmul(float a, float b) { return __fmul_rn(a, b); }
 template <class T> VQ T ldcg(const T * p) { return __ldcg(p); }
+template <class T> VQ T ldg(const T * p) { return __ldg(p); }
 /* A pointer that went through the argument list of an out-of-line function is a generic pointer: every access
    becomes a generic LD/ST.  Re-derive it from the dynamic shared array so that the compiler knows the address
    space again (LDS / STS, vector widths) -- measured 8 % of the whole kernel on idle_passA. */
@@ -746,9 +747,12 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 			unsigned hard = 0;
 #pragma unroll
 			for (int q = 0; q < 3; q++) {
-				v[q] = c_tab.soft[q][gi];
+				/* per-lane index: from global memory (L1/L2), not the constant bank, which would serialise the 32
+				   distinct addresses of a symbol batch -- the largest stall of the burst path on the per-channel chain */
+				v[q] = kp.soft ? vw::ldg(kp.soft + q * 260 + gi) : c_tab.soft[q][gi];
 				const int b = 3 * si + q;
-				const unsigned sb = (c_tab.scr[(b >> 5) & (VDL2_SCR_WORDS - 1)] >> (b & 31)) & 1u;
+				const unsigned sw_ = kp.soft ? vw::ldg(kp.scr + ((b >> 5) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[(b >> 5) & (VDL2_SCR_WORDS - 1)];
+				const unsigned sb = (sw_ >> (b & 31)) & 1u;
 				V[q] = sb ? vw::fsub(1.0f, v[q]) : v[q];	/* descrambler, d8psk.c:54-65 */
 				hard |= (V[q] > 0.5f ? 1u : 0u) << q;
 			}

@@ -50,6 +50,7 @@ struct vdl2gpu {
 	float4 *d_wtab;
 	float4 *d_dcorr;
 	uint4 *d_w8;		/* integer mixer tables (dp4a mode only) */
+	float *d_soft;		/* soft-demap tables for per-lane look-ups */
 	int dp4a;		/* 1: cu8/cs8 at a rate whose dumps are 23/24 samples -> integer dot-product mixer */
 	int sched_slot;
 	unsigned *d_ticket;
@@ -282,6 +283,13 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	unsigned sched_dump[VDL2_DUMPS_PER_ROW];
 	build_tables(*tab, sched_dump, h);
 	e = (cudaError_t) vdl2_kernel_upload_tables(tab);
+	h->d_soft = NULL;
+	if (e == cudaSuccess)
+		e = cudaMalloc(&h->d_soft, sizeof tab->soft + sizeof tab->scr);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(h->d_soft, tab->soft, sizeof tab->soft, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy((char *)h->d_soft + sizeof tab->soft, tab->scr, sizeof tab->scr, cudaMemcpyHostToDevice);
 	delete tab;
 	if (e == cudaSuccess) {
 		/* the dump schedule depends on (fs, SDRCLK, format): handles with the same signature share a
@@ -547,6 +555,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
 	cudaFree(h->d_w8);
+	cudaFree(h->d_soft);
 	cudaFree(h->d_ticket);
 	cudaFree(h->d_progress);
 	cudaFree(h->d_slotmask);
@@ -622,6 +631,8 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.wtab = h->d_wtab;
 	kp.dcorr = h->d_dcorr;
 	kp.w8 = h->d_w8;
+	kp.soft = h->d_soft;
+	kp.scr = (const unsigned *)((const char *)h->d_soft + sizeof(((Vdl2Tables *) 0)->soft));
 	kp.sched_slot = h->sched_slot;
 	kp.ticket = h->d_ticket;
 	kp.ticket_sel = (int)(h->launch_seq % 3u);
