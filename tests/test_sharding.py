@@ -8,7 +8,7 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle.pyoracle import Oracle
+from oracle.pyoracle import Oracle, link_decode
 from tests import emul
 from tests.parity_util import make_channels
 from vdlm2dec_b200 import shard
@@ -33,8 +33,9 @@ def _worker(rank, world, port, q):
     blocks = _demod_shard(mine, specs, iq)
     t = shard.max_over_ranks(1.0 + rank)
     merged = shard.gather_blocks(blocks)
+    frames = shard.gather_frames(link_decode("port", blocks)[0])     # row f1: every rank runs the block pipeline on its own blocks
     if rank == 0:
-        q.put((t, merged.tobytes(), len(merged)))
+        q.put((t, merged.tobytes(), len(merged), frames.tobytes(), len(frames)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,10 +58,12 @@ def test_two_rank_gloo_union_equals_single_rank():
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    t, raw, n = q.get(timeout=300)
+    t, raw, n, fraw, nf = q.get(timeout=300)
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert t == 2.0  # max over ranks
     specs, iq = make_channels(NCH, NS, seed=8)
     single = shard.merge_blocks([_demod_shard(list(range(NCH)), specs, iq)])
     assert n == len(single) > 0 and raw == single.tobytes()
+    fsingle = shard.merge_frames([link_decode("port", single)[0]])
+    assert nf == len(fsingle) > 0 and fraw == fsingle.tobytes()

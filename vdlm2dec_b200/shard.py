@@ -47,3 +47,25 @@ def gather_blocks(blocks: np.ndarray) -> np.ndarray | None:
     out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
     dist.gather_object(blocks, out, dst=0)
     return merge_blocks(out) if dist.get_rank() == 0 else None
+
+
+def merge_frames(per_rank_frames: list[np.ndarray]) -> np.ndarray:
+    """Union of the ranks' frames (row f1: what the reference hands to out()) in the order vdl2_drain_frames uses on
+    one GPU: oldest trigger first, then channel, then position inside the block.  `block` is rank-local and is reset
+    to -1: chn / Fr / ppm / sync_dump travel in the frame."""
+    parts = [f for f in per_rank_frames if len(f)]
+    if not parts:
+        return per_rank_frames[0]
+    allf = np.concatenate(parts).copy()
+    allf["block"] = -1
+    return allf[np.lexsort((allf["len"], allf["chn"], allf["sync_dump"]))]
+
+
+def gather_frames(frames: np.ndarray) -> np.ndarray | None:
+    """all ranks -> rank 0 (returns None elsewhere); single process: identity."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return merge_frames([frames])
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(frames, out, dst=0)
+    return merge_frames(out) if dist.get_rank() == 0 else None
