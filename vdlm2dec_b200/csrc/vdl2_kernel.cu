@@ -16,10 +16,15 @@
  *     conflict free.  Bytes are widened with PRMT magic-number tricks (exact), the complex
  *     MAC runs as packed FFMA2 on sample pairs; dumps go, in time order, to a per-warp scratch that
  *     stays L2 resident (21.6 KB per warp), which keeps shared memory per warp at 13 KB -> 16 warps/SM.
+ *     8-bit input at 2 Msps (the RTL path) takes the integer dot-product mixer instead: per-dump TMA
+ *     windows, IDP.4A with three weight digits, no conversion (mix_rows_dp4a below).
  *   phase 2 (demodulator): vdl2_demod.cuh, lanes over consecutive steps / symbols.
  *
  * Phase 1 needs no channel state, so a warp mixes tile t of a channel while another warp
- * still demodulates tile t-1; only phase 2 waits on the per-channel progress flag.
+ * still demodulates tile t-1; only phase 2 waits on the per-channel progress flag, and while it
+ * would wait it runs pass A of the idle search speculatively (stage 0 of the two-stage loop in the
+ * kernel, IdlePre in vdl2_demod.cuh).  Consecutive launches may overlap (programmatic dependent
+ * launch): progress counts tiles since create, the work counters rotate, scratch slots are per SM.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
