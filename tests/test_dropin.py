@@ -16,6 +16,8 @@ from vdlm2dec_b200 import synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_cpu")
 GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu")
+AIR_CPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_cpu")   # air.c + fake libairspy
+AIR_GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_gpu")
 LINK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu_link")   # shim also replaces vdlm2.o + rs.o (row f1)
 ALL = ("-G", "-E", "-U")  # print ground, empty and undecoded frames too
 needs_bins = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(GPU_BIN)), reason="drop-in binaries not built")
@@ -149,3 +151,70 @@ def test_dropin_block_pipeline_on_device(tmp_path):
     assert len(jb) == _expected_blocks(cap, [-50_000, -175_000]) and ja == jb
     cap2, _ = _capture(tmp_path, [-50_000], seed=5)
     assert _messages(_run(GPU_BIN, cap2, ["136.975"], extra=ALL)[0]) == _messages(_run(LINK_BIN, cap2, ["136.975"], extra=ALL)[0])
+
+
+def _air_capture(tmp_path, fr_mhz=("136.975",), fs=6_000_000, nblk=128, seed=9):
+    """float32 REAL samples as air.c asks for them (AIRSPY_SAMPLE_FLOAT32_REAL, air.c:123).  air.c tunes to Fc (chooseFc,
+    air.c:48-70) and mixes with Fo = Fr - (Fc + fs/4) (air.c:180-185); at 6 Msps and one frequency Fc = Fr, so Fo = -fs/4."""
+    n = 32768 * nblk
+    frs = [int(round(float(f) * 1e6)) for f in fr_mhz]
+    off = 0
+    if fs == 5_000_000:     # chooseFc, air.c:48-70: the R820T2 IF filter pair of the Airspy R2 shifts the tuning
+        hf = [1953050, 1980748, 2001344, 2032592, 2060291, 2087988]
+        lf = [525548, 656935, 795424, 898403, 1186034, 1502073, 1715133, 1853622]
+        bw = max(frs) - min(frs) + 2 * 25_000
+        i = next(i for i in range(7, -1, -1) if hf[5] - lf[i] >= bw)
+        j = next((j for j in range(5, -1, -1) if hf[j] - lf[i] <= bw), -1) + 1
+        off = (hf[j] + lf[i]) // 2 - fs // 4
+    fc = ((max(frs) + min(frs)) // 2 + off + 12_500) // 25_000 * 25_000
+    fos = [f - (fc + fs // 4) for f in frs]
+    x = np.zeros(n, dtype=np.float64)
+    for i, fo in enumerate(fos):
+        spec = synth.standard_channel(seed=seed * 10 + i, nsamples=n - 200_000, Fo=fo, fs=fs, period=int(0.03 * fs), payload_bytes=(20, 300),
+                                      amp=(40.0, 60.0), noise_sigma=0.0)
+        x += synth.render_channel(spec, n, fs=fs, fmt="f32real").astype(np.float64)
+    rng = np.random.default_rng(seed)
+    x += (4.0 / 64.0) * rng.standard_normal(n)
+    path = tmp_path / "cap.f32"
+    x.astype(np.float32).tofile(path)
+    return str(path), fos
+
+
+def _air_run(binary, cap, freqs, fs, extra=ALL):
+    env = dict(os.environ, VDL2_FAKE_IQ=cap, VDL2_FAKE_RATE=str(fs))
+    p = subprocess.run([binary, *extra, "-v", *freqs], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 1, p.stderr[-2000:]
+    return p.stdout, p.stderr
+
+
+def _air_expected(cap, fos, fs):
+    from oracle.pyoracle import Oracle
+    x = np.fromfile(cap, dtype=np.float32)
+    x = x[:len(x) // 32768 * 32768]         # rx_callback hands over whole 32768-sample blocks only (air.c:199-214)
+    return sum(len(Oracle("port", Fo=fo, fs=fs, sdrclk=fs // 4000, real_input=True).feed(x, "f32real").blocks) for fo in fos)
+
+
+needs_air = pytest.mark.skipif(not (os.path.exists(AIR_CPU_BIN) and os.path.exists(AIR_GPU_BIN)), reason="Airspy drop-in binaries not built")
+
+
+@needs_air
+@pytest.mark.parametrize("fs", [6_000_000, 5_000_000])
+def test_air_cpu_binary_decodes_synthetic_capture(tmp_path, fs):
+    """The all-reference Airspy build (air.c, rx_callback re-blocking of 49152-sample transfers) accepts the synthetic
+    real-sample capture -- runs without a GPU."""
+    cap, fos = _air_capture(tmp_path, fs=fs)
+    out, err = _air_run(AIR_CPU_BIN, cap, ["136.975"], fs)
+    assert "fakeairspy: Fc=" in err
+    assert len(_messages(out)) == _air_expected(cap, fos, fs) > 5  # every burst the oracle completes is printed
+
+
+@pytest.mark.gpu
+@needs_air
+@pytest.mark.parametrize("fs", [6_000_000, 5_000_000])
+def test_air_dropin_text_identical(tmp_path, fs):
+    """the same shim object built with -DWITH_AIR (float Cbuff, real samples, SDRCLK = fs/4000) in place of
+    d8psk.o in the reference's Airspy build: identical text."""
+    cap, fos = _air_capture(tmp_path, fs=fs)
+    a = _messages(_air_run(AIR_CPU_BIN, cap, ["136.975"], fs)[0])
+    b = _messages(_air_run(AIR_GPU_BIN, cap, ["136.975"], fs)[0])
+    assert len(b) == _air_expected(cap, fos, fs) > 5 and a == b
