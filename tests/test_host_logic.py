@@ -41,6 +41,12 @@ def test_struct_layouts_match_header():
     assert C.sizeof(api.ChanParam) == 12  # thread_param_t, vdlm2.h:49-52
     assert api.BLOCK_DT.itemsize == 2080 and api.BLOCK_DT.fields["data"][1] == 36
     assert api.SYM_DT.itemsize == 40 and api.SYNC_DT.itemsize == 24 and api.STEP_DT.itemsize == 24
+    # row f1 records: vdl2_frame_t (2048 B, hdata at 32) and vdl2_blkstat_t (16 B); the oracle mirrors must agree
+    from oracle import pyoracle
+    assert api.FRAME_DT.itemsize == 2048 and api.FRAME_DT.fields["hdata"][1] == 32 and api.FRAME_DT == pyoracle.FRAME_DT
+    assert api.BLKSTAT_DT.itemsize == 16 and api.BLKSTAT_DT == pyoracle.BLKSTAT_DT
+    hdr = open(os.path.join(ROOT, "include", "vdl2gpu.h")).read()
+    assert "uint8_t hdata[2016];" in hdr and "} vdl2_frame_t;" in hdr and "#define VDL2_ABI_VERSION 2" in hdr
 
 
 @pytest.mark.parametrize("tile", [2688, 84, 84 * 5, 1000])
