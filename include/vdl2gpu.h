@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VDL2_ABI_VERSION 2
+#define VDL2_ABI_VERSION 3
 
 /* input sample formats; CU8 is what rtl.c receives (rtl.c:287-289: x - 127.37f),
    CF32 is the already converted Cbuff of the reference (vdlm2.h:89),
@@ -189,6 +189,13 @@ int vdl2_link_decode(vdl2gpu_t * h, const vdl2_block_t * blocks, int nblocks, vd
    the blocks themselves in the same order (frame.block indexes them; -1 when the blocks were not asked for) */
 int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int *n_frames, vdl2_block_t * blocks, int max_blocks,
 		      int *n_blocks);
+
+/* ---- ingest: page-locked host memory for the buffers handed to vdl2_process_host().
+   From such a buffer the upload runs at the PCIe rate without the driver's staging copy; a replay front end
+   (file_shim.c: initFile / runFileSample, vdlm2.h:110-111) keeps a ring of them so that reading the capture
+   overlaps the demodulation of the previous batch.  Needs a usable device like every other entry point. ---- */
+int vdl2_host_alloc(size_t bytes, void **out);
+int vdl2_host_free(void *p);
 
 int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
 /* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */

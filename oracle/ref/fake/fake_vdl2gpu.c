@@ -1,0 +1,87 @@
+/* TEST INFRASTRUCTURE ONLY -- never part of the product, never linked into libvdl2gpu.so.
+ *
+ * A stand-in for the handful of libvdl2gpu entry points the drop-in shims call, answering from the CPU oracle
+ * (oracle/libvdl2port.so).  Purpose: the HOST logic of the replay front end (vdlm2dec_b200/csrc/file_shim.c +
+ * d8psk_shim.c -DVDL2_SHIM_FILE: argument seam, centre-frequency rule, reader ring, batching, the rtl.c index
+ * quirk, hand-off to decodeVdlm2) can be checked against the all-reference binary in the CPU test tier, where
+ * there is no GPU (tests/test_replay.py::test_replay_host_logic_*).  The binary built from it is
+ * oracle/_ref/vdlm2dec_file_hostcheck; the product binaries link the real library and fail loudly without a
+ * device. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "vdl2gpu.h"
+#include "../../orc_api.h"
+
+struct vdl2gpu {
+	vdl2_config_t cfg;
+	void *orc[8];
+};
+
+int vdl2_abi_version(void) { return VDL2_ABI_VERSION; }
+const char *vdl2_last_error(const vdl2gpu_t * h) { (void)h; return "fake_vdl2gpu"; }
+
+int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, vdl2gpu_t ** out)
+{
+	if (cfg->nch > 8 || cfg->ch_per_stream != cfg->nch)
+		return 1;
+	vdl2gpu_t *h = calloc(1, sizeof *h);
+	h->cfg = *cfg;
+	for (int c = 0; c < cfg->nch; c++)
+		h->orc[c] = orc_open(chans[c].chn, chans[c].Fr, chans[c].Fo, cfg->fs, cfg->sdrclk, cfg->format == VDL2_FMT_F32REAL, ORC_TAP_BLOCKS);
+	*out = h;
+	return 0;
+}
+
+int vdl2_destroy(vdl2gpu_t * h)
+{
+	for (int c = 0; c < h->cfg.nch; c++)
+		orc_close(h->orc[c]);
+	free(h);
+	return 0;
+}
+
+int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t n, size_t pitch)
+{
+	(void)pitch;
+	if (n > h->cfg.max_samples)
+		return 1;
+	for (int c = 0; c < h->cfg.nch; c++)
+		switch (h->cfg.format) {
+		case VDL2_FMT_CU8: orc_feed_cu8(h->orc[c], iq, n, (float)127.37); break;
+		case VDL2_FMT_CS8: orc_feed_cs8(h->orc[c], iq, n); break;
+		case VDL2_FMT_CS16: orc_feed_cs16(h->orc[c], iq, n); break;
+		case VDL2_FMT_CF32: orc_feed_cf32(h->orc[c], iq, n); break;
+		default: orc_feed_f32real(h->orc[c], iq, n); break;
+		}
+	return 0;
+}
+
+static int by_trigger(const void *a, const void *b)
+{
+	const vdl2_block_t *x = a, *y = b;
+	if (x->sync_dump != y->sync_dump)
+		return x->sync_dump < y->sync_dump ? -1 : 1;
+	return x->chn - y->chn;
+}
+
+int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out)
+{
+	int n = 0;
+	for (int c = 0; c < h->cfg.nch; c++) {
+		size_t k = 0;
+		const orc_block *b = orc_tap(h->orc[c], ORC_TAP_BLOCKS, &k);
+		if (n + (int)k > max)
+			return 1;
+		if (k)
+			memcpy(out + n, b, k * sizeof *b);	/* orc_block and vdl2_block_t share one layout (2080 B) */
+		n += (int)k;
+		orc_clear_taps(h->orc[c]);
+	}
+	qsort(out, n, sizeof *out, by_trigger);
+	*n_out = n;
+	return 0;
+}
+
+int vdl2_host_alloc(size_t bytes, void **out) { *out = malloc(bytes); return *out == NULL; }
+int vdl2_host_free(void *p) { free(p); return 0; }

@@ -61,7 +61,7 @@ class Stats(C.Structure):
 EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
            "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
-           "vdl2_drain_frames"]
+           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free"]
 
 _lib = None
 
@@ -89,6 +89,8 @@ def load_library():
     lib.vdl2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.vdl2_link_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     lib.vdl2_drain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.vdl2_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.vdl2_host_free.argtypes = [C.c_void_p]
     lib.vdl2_cuda_stream.restype = C.c_void_p
     lib.vdl2_cuda_stream.argtypes = [C.c_void_p]
     _lib = lib

@@ -23,14 +23,20 @@
  * no blk_thread is started, and instead of handing blocks to decodeVdlm2() the leader drains FRAMES -- the
  * blocks went through rs(), HDLC un-stuffing and the FCS check on the device (vdl2_drain_frames) -- and calls
  * out(blk, hdata, l) (vdlm2.h:134) exactly where check_frame() would (vdlm2.c:60).
+ *
+ * -DVDL2_SHIM_FILE (row f2, file replay): the object is linked next to file_shim.o, which takes the place of
+ * rtl.o.  There is no SDR callback and no Cbuff then: the workers only register their channel and park on the
+ * barrier; file_shim.c feeds raw captures through vdl2shim_open() / vdl2shim_feed() below (shim_internal.h).
  */
 #define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include "vdlm2.h"		/* the reference's header, found through -I */
 #include "vdl2gpu.h"
+#include "shim_internal.h"
 
 extern int nbch;		/* main.c:59 */
 
@@ -73,25 +79,52 @@ static void die(const char *what)
 	exit(1);
 }
 
-static void gpu_open(void)
+int vdl2shim_nch(void)
+{
+	return nbch;
+}
+
+/* blocks / frames pending between two drains never exceed the queue, so one drain call always has room */
+#define SHIM_QCAP 4096
+static vdl2_block_t *g_blocks;
+static vdl2_frame_t *g_frames;
+static int g_last_n;		/* blocks handed over by the last vdl2shim_feed() */
+static double g_t0 = -1;	/* VDL2_FILE_T0: epoch of sample 0 of a replayed capture; < 0 = wall clock as in d8psk.c:295 */
+
+void vdl2shim_open(unsigned fs, unsigned sdrclk, int format, size_t max_samples)
 {
 	vdl2_config_t cfg;
 	memset(&cfg, 0, sizeof cfg);
-	cfg.fs = SDRINRATE;
-	cfg.sdrclk = SDRCLK;
-#ifdef WITH_AIR
-	cfg.format = VDL2_FMT_F32REAL;
-#else
-	cfg.format = VDL2_FMT_CF32;
-#endif
+	cfg.fs = fs;
+	cfg.sdrclk = sdrclk;
+	cfg.format = format;
 	cfg.nch = nbch;
 	cfg.ch_per_stream = nbch;
 	cfg.device = getenv("VDL2_GPU_DEVICE") ? atoi(getenv("VDL2_GPU_DEVICE")) : 0;
-	cfg.max_samples = RTLINBUFSZ / 2 + SDRINRATE / 1000;
-	cfg.max_blocks = 1024;
+	cfg.max_samples = max_samples + fs / 1000;	/* room for the carried sub-millisecond tail */
+	cfg.max_blocks = SHIM_QCAP;
 	if (vdl2_create(&cfg, g_par, &g_gpu))
 		die("vdl2_create");
+	g_blocks = malloc(sizeof(vdl2_block_t) * SHIM_QCAP);
+	g_frames = malloc(sizeof(vdl2_frame_t) * SHIM_QCAP);
+	if (!g_blocks || !g_frames) {
+		fprintf(stderr, "vdl2gpu shim: out of memory\n");
+		exit(1);
+	}
+	if (getenv("VDL2_FILE_T0"))
+		g_t0 = atof(getenv("VDL2_FILE_T0"));
 	atexit(quiesce);
+}
+
+static void stamp(struct timeval *tv, int64_t sync_dump)
+{				/* d8psk.c:295 takes the wall clock at the trigger; a replay can ask for capture time instead */
+	if (g_t0 < 0) {
+		gettimeofday(tv, NULL);
+		return;
+	}
+	const double t = g_t0 + (double)sync_dump / 84000.0;	/* 8 x 10500 decimated samples per second (d8psk.h) */
+	tv->tv_sec = (time_t) t;
+	tv->tv_usec = (suseconds_t) ((t - (double)tv->tv_sec) * 1e6);
 }
 
 #ifdef VDL2_SHIM_LINK
@@ -113,14 +146,18 @@ void stopVdlm2(void)
 {				/* main.c:108,244: nothing is queued on the host */
 }
 
-static void gpu_block(void)
+void vdl2shim_finish(void)
+{				/* out() ran synchronously inside vdl2shim_feed(): nothing is pending */
+}
+
+void vdl2shim_feed(const void *iq, size_t nsamples)
 {
-	static vdl2_frame_t fr[1024];
+	vdl2_frame_t *fr = g_frames;
 	int nf = 0, nb = 0;
 	pthread_mutex_lock(&g_busy);
-	if (vdl2_process_host(g_gpu, Cbuff, RTLINBUFSZ / 2, 0))
+	if (vdl2_process_host(g_gpu, iq, nsamples, 0))
 		die("vdl2_process_host");
-	if (vdl2_drain_frames(g_gpu, fr, 1024, &nf, NULL, 0, &nb))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
+	if (vdl2_drain_frames(g_gpu, fr, SHIM_QCAP, &nf, NULL, 0, &nb))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
 		die("vdl2_drain_frames");
 	for (int i = 0; i < nf; i++) {
 		msgblk_t blk;	/* what check_frame() passes on (vdlm2.c:60): only the header fields are read downstream */
@@ -128,20 +165,20 @@ static void gpu_block(void)
 		blk.chn = fr[i].chn;
 		blk.Fr = fr[i].Fr;
 		blk.ppm = fr[i].ppm;
-		gettimeofday(&blk.tv, NULL);	/* d8psk.c:295 (wall clock in the reference too) */
+		stamp(&blk.tv, fr[i].sync_dump);
 		out(&blk, fr[i].hdata, fr[i].len);
 	}
 	pthread_mutex_unlock(&g_busy);
 }
 #else
-static void gpu_block(void)
+void vdl2shim_feed(const void *iq, size_t nsamples)
 {
-	static vdl2_block_t out[1024];
+	vdl2_block_t *out = g_blocks;
 	int n = 0;
 	pthread_mutex_lock(&g_busy);
-	if (vdl2_process_host(g_gpu, Cbuff, RTLINBUFSZ / 2, 0))
+	if (vdl2_process_host(g_gpu, iq, nsamples, 0))
 		die("vdl2_process_host");
-	if (vdl2_drain_blocks(g_gpu, out, 1024, &n))
+	if (vdl2_drain_blocks(g_gpu, out, SHIM_QCAP, &n))
 		die("vdl2_drain_blocks");
 	for (int i = 0; i < n; i++) {
 		channel_t *ch = NULL;
@@ -151,7 +188,7 @@ static void gpu_block(void)
 		if (!ch)
 			continue;
 		msgblk_t *blk = ch->blk;
-		gettimeofday(&blk->tv, NULL);	/* d8psk.c:295 (wall clock in the reference too) */
+		stamp(&blk->tv, out[i].sync_dump);
 		blk->ppm = out[i].ppm;
 		blk->nbrow = out[i].nbrow;
 		blk->nlbyte = out[i].nlbyte;
@@ -159,7 +196,17 @@ static void gpu_block(void)
 			memcpy(blk->data[r], out[i].data[r], 255);
 		decodeVdlm2(ch);	/* takes blk, installs a fresh zeroed one (vdlm2.c:189-205) */
 	}
+	g_last_n = n;
 	pthread_mutex_unlock(&g_busy);
+}
+
+void vdl2shim_finish(void)
+{
+	/* The reference's stopVdlm2() (vdlm2.c:182-187) waits for its queue to be EMPTY, not for the block blk_thread
+	   has already taken off it, and main() exits right after (main.c:244-246).  A dongle delivers blocks over time;
+	   a replay can hand over its whole last batch at the very end, so give the consumer time for it (about 50 us per
+	   block on a current core) before the caller goes on to stopVdlm2(). */
+	usleep(100000 + 500 * (unsigned)g_last_n);
 }
 #endif
 
@@ -177,14 +224,22 @@ void *rcv_thread(void *arg)
 	g_ch[param->chn] = ch;
 
 	pthread_barrier_wait(&Bar1);	/* all nbch workers have registered once this returns */
+#ifdef VDL2_SHIM_FILE
+	pthread_barrier_wait(&Bar2);	/* parked for good: runFileSample() (file_shim.c) does all the work and main() exits */
+#else
 	const int leader = (param->chn == 0);
 	if (leader)
-		gpu_open();
+#ifdef WITH_AIR
+		vdl2shim_open(SDRINRATE, SDRCLK, VDL2_FMT_F32REAL, RTLINBUFSZ / 2);
+#else
+		vdl2shim_open(SDRINRATE, SDRCLK, VDL2_FMT_CF32, RTLINBUFSZ / 2);
+#endif
 	do {
 		pthread_barrier_wait(&Bar2);
 		if (leader)
-			gpu_block();
+			vdl2shim_feed(Cbuff, RTLINBUFSZ / 2);
 		pthread_barrier_wait(&Bar1);
 	} while (1);
+#endif
 	return NULL;
 }

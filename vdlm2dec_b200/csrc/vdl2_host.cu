@@ -785,6 +785,28 @@ extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int
 	return 0;
 }
 
+/* ---- ingest: page-locked host buffers (row f2) ---- */
+extern "C" int vdl2_host_alloc(size_t bytes, void **out)
+{
+	if (!out || !bytes)
+		return fail(nullptr, "vdl2_host_alloc: null argument");
+	*out = nullptr;
+	cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess)
+		return fail(nullptr, "vdl2_host_alloc: %zu bytes: %s", bytes, cudaGetErrorString(e));
+	return 0;
+}
+
+extern "C" int vdl2_host_free(void *p)
+{
+	if (!p)
+		return 0;
+	cudaError_t e = cudaFreeHost(p);
+	if (e != cudaSuccess)
+		return fail(nullptr, "vdl2_host_free: %s", cudaGetErrorString(e));
+	return 0;
+}
+
 /* ---- block pipeline ---- */
 static int link_reserve(vdl2gpu * h, int nblocks, int nframes, bool own_blocks)
 {
