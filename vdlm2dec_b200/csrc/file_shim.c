@@ -37,6 +37,7 @@
 #include <string.h>
 #include <strings.h>
 #include <semaphore.h>
+#include <time.h>
 #include "vdlm2.h"		/* the reference's header, found through -I */
 #include "vdl2gpu.h"
 #include "shim_internal.h"
@@ -185,6 +186,8 @@ int runFileSample(void)
 	pthread_create(&th, NULL, reader, NULL);
 
 	unsigned long long total = 0;
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);	/* handle and ring exist: what follows is the steady state of a replay */
 	for (int k = 0;; k ^= 1) {
 		sem_wait(&g_full);
 		const size_t n = g_slot[k].nsamples;
@@ -201,9 +204,13 @@ int runFileSample(void)
 			break;
 	}
 	pthread_join(th, NULL);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
 	vdl2shim_finish();
-	if (verbose > 1)
-		fprintf(stderr, "Replayed %llu samples\n", total);
+	if (verbose > 1) {
+		const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+		fprintf(stderr, "Replayed %llu samples in %.4f s (%.1f Msamples/s per channel, %d channels)\n", total, dt,
+			dt > 0 ? 1e-6 * (double)total / dt : 0.0, vdl2shim_nch());
+	}
 	fclose(g_file);
 	g_file = NULL;
 	return 0;
