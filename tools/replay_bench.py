@@ -12,7 +12,7 @@ import tempfile
 import time
 
 sys.path.insert(0, ".")
-from tools.dropin_bench import capture
+from tests.test_dropin import _capture
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = os.path.join(ROOT, "oracle", "_ref")
@@ -25,8 +25,11 @@ if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as d:
         fmax = max(float(f) for f in FREQS)
         fos = [int(round((float(f) - fmax) * 1e6)) - 50_000 for f in FREQS]
-        base = os.path.join(d, "base.cu8")
-        n = capture(base, fos, nblk) * rep
+        # well-formed ACARS-over-AVLC payloads: random ones that happen to look like XID groups send the reference's outxid()
+        # (outxid.c:268-299, signed 16-bit group length) into an endless loop, which stops its single consumer thread
+        import pathlib
+        base, _ = _capture(pathlib.Path(d), fos, nblk=nblk, seed=7, acars=True)
+        n = 32768 * nblk * rep
         data = open(base, "rb").read()
         cap = os.path.join(d, "full.cu8")
         with open(cap, "wb") as g:
@@ -43,10 +46,12 @@ if __name__ == "__main__":
                 if not os.path.exists(b):
                     continue
                 t0 = time.perf_counter()
-                p = subprocess.run([b, "-G", "-E", "-U", "-v", "-r", cap, *FREQS[:nch]], env=dict(os.environ, **env), capture_output=True, text=True)
+                # no -v: at verbose 2 the reference's own hex dump of XID-looking payloads overruns its 50000-byte text buffer (outxid.c:296 ->
+                # out.c:381,396) and the program -- all-reference build included -- dies on this capture's random payloads
+                p = subprocess.run([b, "-G", "-E", "-U", "-r", cap, *FREQS[:nch]], env=dict(os.environ, VDL2_FILE_STATS="1", **env), capture_output=True, text=True)
                 wall = time.perf_counter() - t0
                 m = re.search(r"Replayed (\d+) samples in ([0-9.]+) s", p.stderr)
-                rec = {"channels": nch, "binary": name, "samples": n, "wall_seconds": round(wall, 3), "messages": p.stdout.count("[#")}
+                rec = {"channels": nch, "rc": p.returncode, "binary": name, "samples": n, "wall_seconds": round(wall, 3), "messages": p.stdout.count("[#")}
                 if m:
                     dt = float(m.group(2))
                     rec.update(replay_seconds=dt, stream_msps=round(1e-6 * int(m.group(1)) / dt, 1),
@@ -60,10 +65,12 @@ if __name__ == "__main__":
             if not os.path.exists(b):
                 continue
             t0 = time.perf_counter()
-            p = subprocess.run([b, "-G", "-E", "-U", "-v", "-r", "0", FREQS[0]], env=dict(os.environ, VDL2_FAKE_IQ=cap), capture_output=True, text=True)
-            wall = time.perf_counter() - t0
-            out.append({"channels": 1, "binary": name, "samples": n, "wall_seconds": round(wall, 3), "messages": p.stdout.count("[#"),
-                        "stream_msps_incl_startup": round(1e-6 * n / wall, 1)})
-            print(json.dumps(out[-1]), flush=True)
+            for nch in (1, 8):
+              t0 = time.perf_counter()
+              p = subprocess.run([b, "-G", "-E", "-U", "-r", "0", *FREQS[:nch]], env=dict(os.environ, VDL2_FAKE_IQ=cap), capture_output=True, text=True)
+              wall = time.perf_counter() - t0
+              out.append({"channels": nch, "rc": p.returncode, "binary": name, "samples": n, "wall_seconds": round(wall, 3), "messages": p.stdout.count("[#"),
+                          "stream_msps_incl_startup": round(1e-6 * n / wall, 1)})
+              print(json.dumps(out[-1]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "replay_bench.json"), "w"), indent=1)

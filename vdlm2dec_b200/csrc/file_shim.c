@@ -20,7 +20,8 @@
  *                                                      thread fills one while the other is being demodulated
  *
  * Capture format: by file extension -- .cu8 (default) .cs8 .cs16 .cf32 -- or VDL2_FILE_FORMAT; 2 Msps unless
- * VDL2_FILE_RATE says otherwise (SDRCLK = rate / 4000, as air.c:138 does for its rates).
+ * VDL2_FILE_RATE says otherwise (SDRCLK = rate / 4000, as air.c:138 does for its rates).  With -v or
+ * VDL2_FILE_STATS=1 the sample count and the steady-state rate of the replay are reported on stderr at the end.
  *
  * VDL2_RTL_QUIRK=1 (cu8 only) reproduces what the reference's callback does to the stream (rtl.c:285-292: the
  * index is incremented before the store, so slot 0 of every block keeps its zero and the last sample of the
@@ -206,7 +207,7 @@ int runFileSample(void)
 	pthread_join(th, NULL);
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	vdl2shim_finish();
-	if (verbose > 1) {
+	if (verbose > 1 || getenv("VDL2_FILE_STATS")) {
 		const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 		fprintf(stderr, "Replayed %llu samples in %.4f s (%.1f Msamples/s per channel, %d channels)\n", total, dt,
 			dt > 0 ? 1e-6 * (double)total / dt : 0.0, vdl2shim_nch());
