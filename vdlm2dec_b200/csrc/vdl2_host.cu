@@ -755,6 +755,29 @@ extern "C" int vdl2_sync(vdl2gpu_t * h)
 	return 0;
 }
 
+/* Stable sort of large fixed-size records (2 KB blocks and frames): order an index array, then gather once.
+   Sorting the records by value moves every one of them log2(n) times -- 34 ms of host time for the 4 500
+   frames of one bench step, against 0.1 ms for the kernel that produced them. */
+template < class T, class Less > static void sort_records(T * rec, size_t n, Less less)
+{
+	if (n < 2)
+		return;
+	std::vector < uint32_t > idx(n);
+	for (size_t i = 0; i < n; i++)
+		idx[i] = (uint32_t) i;
+	std::stable_sort(idx.begin(), idx.end(),[&](uint32_t a, uint32_t b) {
+			 return less(rec[a], rec[b]);}
+	);
+	size_t first = 0;
+	while (first < n && idx[first] == first)
+		first++;
+	if (first == n)
+		return;		/* already in order */
+	std::vector < T > tmp(rec + first, rec + n);
+	for (size_t i = first; i < n; i++)
+		rec[i] = tmp[idx[i] - first];	/* entries before `first` stay put, so every source index is >= first */
+}
+
 extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out)
 {
 	if (!h || !n_out)
@@ -777,8 +800,8 @@ extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int
 	CK(h, cudaMemset(h->d_outq_count, 0, 4));
 	if (cnt[4])
 		CK(h, cudaMemset(h->d_dropped, 0, 4));
-	std::stable_sort(out, out + n,[](const vdl2_block_t & a, const vdl2_block_t & b) {
-			 return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : a.chn < b.chn;}
+	sort_records(out, (size_t) n,[](const vdl2_block_t & a, const vdl2_block_t & b) {
+		     return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : a.chn < b.chn;}
 	);
 	h->st.blocks_out += n;
 	*n_out = (int)n;
@@ -951,8 +974,8 @@ extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_f
 			frames[i].block = -1;	/* the blocks were not asked for; chn / Fr / ppm / sync_dump travel in the frame */
 	}
 	/* same order either way: by trigger time, then channel, then position inside the block */
-	std::stable_sort(frames, frames + *n_frames,[](const vdl2_frame_t & a, const vdl2_frame_t & b) {
-			 return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : (a.chn != b.chn ? a.chn < b.chn : a.len < b.len);}
+	sort_records(frames, (size_t) * n_frames,[](const vdl2_frame_t & a, const vdl2_frame_t & b) {
+		     return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : (a.chn != b.chn ? a.chn < b.chn : a.len < b.len);}
 	);
 	h->st.blocks_out += n;
 	if (n_blocks)
