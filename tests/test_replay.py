@@ -20,13 +20,15 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.test_dropin import ALL, CPU_BIN, _capture, _messages, _run
+from tests.test_dropin import AIR_CPU_BIN, ALL, CPU_BIN, _air_capture, _air_expected, _air_run, _capture, _messages, _run
 from vdlm2dec_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FILE_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_gpu")            # blocks -> reference blk_thread
 FILE_LINK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_gpu_link")  # block pipeline on the device (row f1)
 HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_hostcheck")  # oracle-backed stand-in, CPU tier only
+AIR_FILE_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_file_gpu")        # -DWITH_AIR: takes the place of air.o
+AIR_HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_file_hostcheck")
 needs_host = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(HOSTCHECK_BIN)), reason="replay host-check binary not built")
 needs_file = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(FILE_BIN) and os.path.exists(FILE_LINK_BIN)),
                                 reason="replay binaries not built")
@@ -158,6 +160,36 @@ def test_centre_frequency_rule_matches_rtl_c(tmp_path):
         assert f"Set center freq. to {rule(fd)}Hz" in p.stderr, (freqs, p.stderr)
 
 
+def _air_replay(binary, cap, freqs, fs, extra=ALL, **env):
+    e = dict(os.environ, VDL2_FILE=cap, VDL2_FILE_RATE=str(fs), **{k: str(v) for k, v in env.items()})
+    p = subprocess.run([binary, *extra, "-v", *freqs], env=e, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 1, p.stderr[-2000:]
+    return p.stdout, p.stderr
+
+
+@pytest.mark.skipif(not (os.path.exists(AIR_CPU_BIN) and os.path.exists(AIR_HOSTCHECK_BIN)), reason="Airspy replay host-check binary not built")
+@pytest.mark.parametrize("fs,freqs", [(6_000_000, ["136.975"]), (5_000_000, ["136.975"]), (5_000_000, ["136.975", "136.725"])])
+def test_air_replay_host_logic_identical(tmp_path, fs, freqs):
+    """Airspy build (file_shim.c -DWITH_AIR in the place of air.o, capture named by VDL2_FILE): same centre frequency as
+    air.c's chooseFc (IF-filter shift at 5 Msps included), same mixer offsets, same text as the all-reference build fed the
+    same float32 real samples by a (fake) Airspy -- for one channel; two channel threads race on the reference's header
+    trellis, so there the oracle's count and a common majority are demanded."""
+    cap, fos = _air_capture(tmp_path, fr_mhz=freqs, fs=fs, nblk=96)
+    ref_out, ref_err = _air_run(AIR_CPU_BIN, cap, freqs, fs)
+    out, err = _air_replay(AIR_HOSTCHECK_BIN, cap, freqs, fs, VDL2_FILE_BATCH=1_000_003)
+    fc = re.search(r"fakeairspy: Fc=(\d+)", ref_err).group(1)
+    assert f"Set freq. to {fc} hz" in err and f"Replayed {96 * 32768} samples" in err
+    a, b = _messages(ref_out), _messages(out)
+    assert len(b) == _air_expected(cap, fos, fs) > 5
+    if len(freqs) == 1:
+        assert a == b
+    else:
+        assert len(set(a) & set(b)) >= len(b) // 2
+    p = subprocess.run([AIR_HOSTCHECK_BIN, "136.975"], env={k: v for k, v in os.environ.items() if k != "VDL2_FILE"},
+                       capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0 and "Name the capture to replay in VDL2_FILE" in p.stderr
+
+
 # ---------------------------------------------------------------- GPU tier: the product binaries
 @pytest.mark.gpu
 @needs_file
@@ -217,3 +249,15 @@ def test_pinned_host_buffers_through_the_abi():
         g.close()
     assert len(res[0]) > 0 and res[0].tobytes() == res[1].tobytes()
     assert lib.vdl2_host_free(p) == 0 and lib.vdl2_host_free(None) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(AIR_CPU_BIN) and os.path.exists(AIR_FILE_BIN)), reason="Airspy replay binaries not built")
+@pytest.mark.parametrize("fs", [6_000_000, 5_000_000])
+def test_air_replay_identical_to_reference(tmp_path, fs):
+    """The Airspy product binary (float32 real samples, 4 B/sample raw to the GPU): same text as the all-reference build."""
+    freqs = ["136.975"]
+    cap, fos = _air_capture(tmp_path, fr_mhz=freqs, fs=fs, nblk=96)
+    a = _messages(_air_run(AIR_CPU_BIN, cap, freqs, fs)[0])
+    b = _messages(_air_replay(AIR_FILE_BIN, cap, freqs, fs, VDL2_FILE_BATCH=1_000_003)[0])
+    assert len(b) == _air_expected(cap, fos, fs) > 5 and a == b

@@ -29,6 +29,14 @@
  * exactly like rtl.c; the output is then identical to the reference fed the same bytes by a dongle
  * (tests/test_replay.py).  Without it every sample of the capture is demodulated once, in order.
  *
+ * Airspy build (-DWITH_AIR, air.c instead of rtl.c): the object takes the place of air.o the same way -- initAirspy /
+ * runAirspySample (vdlm2.h:106-107), SDRINRATE, SDRCLK, Fc (air.c:37-40).  main.c calls initAirspy(argv, optind, tparam)
+ * after the options (main.c:205), so there is no argument left for a file name: the capture is named by VDL2_FILE.  It
+ * holds float32 REAL samples (AIRSPY_SAMPLE_FLOAT32_REAL, air.c:123) at 6 Msps, or 5 Msps with VDL2_FILE_RATE=5000000
+ * (the two rates air.c accepts, air.c:134-138); the centre follows air.c:48-70 and the mixer offsets are relative to
+ * Fc + fs/4 (air.c:180-185).  rx_callback (air.c:190-217) copies samples unchanged, so there is no indexing mode here;
+ * it only releases whole 32768-sample blocks, whereas the replay also demodulates a trailing partial block.
+ *
  * Errors follow the reference (rtl.c:200-204, main.c:209-213): message on stderr, non-zero return from init,
  * exit(1) once running.
  */
@@ -46,12 +54,19 @@
 extern int nbch;		/* main.c:59 */
 extern int verbose;		/* main.c:36 */
 
+#ifdef WITH_AIR
+unsigned int SDRINRATE = 6000000;	/* air.c:37 */
+unsigned int SDRCLK = 1500;	/* air.c:38 */
+#define DEFAULT_FORMAT VDL2_FMT_F32REAL
+#else
 unsigned int SDRINRATE = 2000000;	/* rtl.c:36 */
 unsigned int SDRCLK = 500;	/* rtl.c:37 */
-unsigned int Fc;		/* rtl.c:39 */
+#define DEFAULT_FORMAT VDL2_FMT_CU8
+#endif
+unsigned int Fc;		/* rtl.c:39, air.c:40 */
 
 static FILE *g_file;
-static int g_format = VDL2_FMT_CU8;
+static int g_format = DEFAULT_FORMAT;
 static int g_quirk;
 static size_t g_batch = (size_t) 1 << 22;	/* samples per launch */
 
@@ -59,6 +74,7 @@ static size_t sample_bytes(int fmt)
 {
 	switch (fmt) {
 	case VDL2_FMT_CS16:
+	case VDL2_FMT_F32REAL:
 		return 4;
 	case VDL2_FMT_CF32:
 		return 8;
@@ -77,6 +93,10 @@ static int format_of(const char *name)
 		return VDL2_FMT_CS8;
 	if (!strcasecmp(name, "cs16") || !strcasecmp(name, "s16"))
 		return VDL2_FMT_CS16;
+#ifdef WITH_AIR
+	if (!strcasecmp(name, "f32real") || !strcasecmp(name, "f32") || !strcasecmp(name, "real"))
+		return VDL2_FMT_F32REAL;
+#endif
 	if (!strcasecmp(name, "cf32") || !strcasecmp(name, "f32") || !strcasecmp(name, "cfile"))
 		return VDL2_FMT_CF32;
 	return -1;
@@ -101,7 +121,13 @@ int initFile(char *file)
 	}
 	if (f < 0)
 		f = format_of(dot ? dot + 1 : NULL);
-	g_format = f < 0 ? VDL2_FMT_CU8 : f;
+	g_format = f < 0 ? DEFAULT_FORMAT : f;
+#ifdef WITH_AIR
+	if (g_format != VDL2_FMT_F32REAL) {	/* the channel offsets of this build are those of a real-sample stream (air.c:180-185) */
+		fprintf(stderr, "The Airspy build replays float32 real captures only\n");
+		return 1;
+	}
+#endif
 	if (getenv("VDL2_FILE_RATE")) {
 		const long r = atol(getenv("VDL2_FILE_RATE"));
 		if (r < 1000000 || r % 4000) {
@@ -217,6 +243,90 @@ int runFileSample(void)
 	return 0;
 }
 
+#ifdef WITH_AIR
+/* ---- the air.o seam, so that the unmodified main.c drives the replay ---- */
+
+/* Centre frequency, the rule of air.c:48-70.  At 5 Msps (Airspy R2) the reference narrows the R820T2 IF filter around the
+   channels and shifts the tuning by the offset of the chosen pass band; the edge frequencies below are the tuner's
+   (air.c:45-46).  There is no tuner to program here, but a capture taken by the reference was tuned this way. */
+static const unsigned int if_hi[6] = { 1953050, 1980748, 2001344, 2032592, 2060291, 2087988 };
+static const unsigned int if_lo[8] = { 525548, 656935, 795424, 898403, 1186034, 1502073, 1715133, 1853622 };
+
+static unsigned int centre_for_real(unsigned int fmin, unsigned int fmax)
+{
+	const unsigned int need = fmax - fmin + 2 * STEPRATE;
+	unsigned int shift = 0;
+	if (SDRINRATE == 5000000) {
+		int lo = 7, hi = 5;
+		while (lo >= 0 && if_hi[5] - if_lo[lo] < need)	/* highest low edge that still leaves room */
+			lo--;
+		if (lo < 0)
+			return 0;
+		while (hi >= 0 && if_hi[hi] - if_lo[lo] > need)	/* lowest high edge that still leaves room */
+			hi--;
+		hi++;
+		if (hi > 5)	/* exact fit of the widest pass band: the reference indexes past its table here */
+			hi = 5;
+		shift = (if_hi[hi] + if_lo[lo]) / 2 - SDRINRATE / 4;
+	}
+	return ((fmax + fmin) / 2 + shift + STEPRATE / 2) / STEPRATE * STEPRATE;
+}
+
+int initAirspy(char **argv, int optind, thread_param_t * param)
+{				/* main.c:205, after the options: argv[optind...] are the frequencies (air.c:84-110) */
+	unsigned int fmin = 140000000, fmax = 0;
+	char *a;
+	nbch = 0;
+	while ((a = argv[optind]) && nbch < MAXNBCHANNELS) {
+		const unsigned int f = (int)(1000000 * atof(a));
+		optind++;
+		if (f < 118000000 || f > 138000000) {
+			fprintf(stderr, "WARNING: Invalid frequency %d\n", f);
+			continue;
+		}
+		param[nbch].chn = nbch;
+		param[nbch].Fr = f;
+		if (f < fmin)
+			fmin = f;
+		if (f > fmax)
+			fmax = f;
+		nbch++;
+	}
+	if (nbch == 0) {
+		fprintf(stderr, "Need a least one frequency\n");
+		return 1;
+	}
+	if (!getenv("VDL2_FILE")) {
+		fprintf(stderr, "Name the capture to replay in VDL2_FILE\n");
+		return 1;
+	}
+	if (initFile(getenv("VDL2_FILE")))
+		return 1;
+	if (SDRINRATE != 5000000 && SDRINRATE != 6000000) {	/* air.c:134-146 */
+		fprintf(stderr, "did not find needed sampling rate\n");
+		return -1;
+	}
+	if (getenv("VDL2_FILE_FC"))
+		Fc = (unsigned int)(1000000 * atof(getenv("VDL2_FILE_FC")));
+	else
+		Fc = centre_for_real(fmin, fmax);
+	if (Fc == 0) {
+		fprintf(stderr, "Frequencies too far apart\n");
+		return 1;
+	}
+	if (verbose > 1)
+		fprintf(stderr, "Set freq. to %d hz\n", Fc);
+	const unsigned int f0 = Fc + SDRINRATE / 4;	/* air.c:180-185 */
+	for (int n = 0; n < nbch; n++)
+		param[n].Fo = param[n].Fr - f0;
+	return 0;
+}
+
+int runAirspySample(void)
+{
+	return runFileSample();
+}
+#else
 /* ---- the rtl.o seam, so that the unmodified main.c drives the replay ---- */
 
 /* Centre frequency for a set of channels, the rule of rtl.c:123-160: sorted ascending; from 50 kHz above the
@@ -295,3 +405,4 @@ int runRtlSample(void)
 {
 	return runFileSample();
 }
+#endif
