@@ -196,6 +196,13 @@ int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int 
    overlaps the demodulation of the previous batch.  Needs a usable device like every other entry point. ---- */
 int vdl2_host_alloc(size_t bytes, void **out);
 int vdl2_host_free(void *p);
+/* Raw cu8 as an RTL dongle delivers it, demodulated the way the REFERENCE sees it: in_callback (rtl.c:285-292) increments
+   its index before the store, so slot 0 of every 32768-sample block keeps its zero, sample k lands in slot k + 1 and the
+   last sample of the block is lost.  The bytes cross PCIe raw (2 B/sample) and are expanded to that complex-float block
+   layout ON THE DEVICE (a zero sample cannot be written in cu8: the conversion is u - 127.37), then demodulated like
+   vdl2_process_host() input.  The handle must have format VDL2_FMT_CF32 and one stream; nsamples must be a whole number
+   of 32768-sample callbacks.  Output is bit-identical to the reference fed the same bytes. */
+int vdl2_process_host_rtl(vdl2gpu_t * h, const void *cu8, size_t nsamples);
 
 int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
 /* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */

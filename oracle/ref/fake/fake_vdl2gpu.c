@@ -57,6 +57,16 @@ int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t n, size_t pitch)
 	return 0;
 }
 
+int vdl2_process_host_rtl(vdl2gpu_t * h, const void *cu8, size_t n)
+{				/* the oracle's own statement of rtl.c:285-292, one callback at a time */
+	if (h->cfg.format != VDL2_FMT_CF32 || n % 32768 || n > h->cfg.max_samples)
+		return 1;
+	for (int c = 0; c < h->cfg.nch; c++)
+		for (size_t b = 0; b < n; b += 32768)
+			orc_feed_rtl_block_quirk(h->orc[c], (const uint8_t *)cu8 + 2 * b);
+	return 0;
+}
+
 static int by_trigger(const void *a, const void *b)
 {
 	const vdl2_block_t *x = a, *y = b;

@@ -77,7 +77,9 @@ def test_replay_host_logic_quirk_identical(tmp_path, freqs, batch):
     fos = _fos(freqs)
     cap, nb = _capture(tmp_path, fos, nblk=40)
     ref_out, ref_err = _run(CPU_BIN, cap, freqs, extra=ALL)
-    out, err = _replay(HOSTCHECK_BIN, cap, freqs, VDL2_RTL_QUIRK=1, VDL2_FILE_BATCH=batch)
+    out, err = _replay(HOSTCHECK_BIN, cap, freqs, VDL2_RTL_QUIRK="host", VDL2_FILE_BATCH=batch)   # file_shim.c's own expansion
+    dev_out, dev_err = _replay(HOSTCHECK_BIN, cap, freqs, VDL2_RTL_QUIRK=1, VDL2_FILE_BATCH=batch)  # vdl2_process_host_rtl seam
+    assert _messages(dev_out) == _messages(out) and "on the device" in dev_err and "on the host" in err
     fc = re.search(r"fakertl: Fc=(\d+)", ref_err).group(1)
     assert f"Set center freq. to {fc}Hz" in err and "rtl.c block indexing" in err
     assert f"Replayed {40 * 32768} samples" in err
@@ -198,8 +200,41 @@ def test_replay_quirk_mode_identical_to_reference(tmp_path):
     freqs = ["136.975"]
     cap, nb = _capture(tmp_path, _fos(freqs), nblk=60)
     a = _messages(_run(CPU_BIN, cap, freqs, extra=ALL)[0])
-    b = _messages(_replay(FILE_BIN, cap, freqs, VDL2_RTL_QUIRK=1, VDL2_FILE_BATCH=400_000)[0])
-    assert len(b) == _expected(cap, _fos(freqs), "rtl_quirk") > 5 and a == b
+    b = _messages(_replay(FILE_BIN, cap, freqs, VDL2_RTL_QUIRK=1, VDL2_FILE_BATCH=400_000)[0])      # expanded on the device
+    c = _messages(_replay(FILE_BIN, cap, freqs, VDL2_RTL_QUIRK="host", VDL2_FILE_BATCH=400_000)[0])  # expanded like rtl.c, on the host
+    assert len(b) == _expected(cap, _fos(freqs), "rtl_quirk") > 5 and a == b and a == c
+
+
+@pytest.mark.gpu
+def test_process_host_rtl_quirk_bit_exact_with_oracle():
+    """vdl2_process_host_rtl through the C ABI: raw cu8 callbacks in, blocks bit exact with the oracle fed the stream as
+    rtl.c:285-292 lays it out, and with the same handle type fed the host-expanded complex floats; in several calls so the
+    sub-millisecond tail (768 samples per callback) is carried across them."""
+    from oracle.pyoracle import Oracle
+    from tests.parity_util import make_channels
+    from vdlm2dec_b200 import api
+    n = 32768 * 24
+    specs, iq = make_channels(1, n, seed=6)
+    fo = specs[0].Fo
+    want = Oracle("port", Fo=fo).feed(iq[0], "rtl_quirk").blocks
+    g = api.Vdl2Gpu([(0, 136_975_000, fo)], fmt="cf32", max_samples=32768 * 8)
+    for k in range(0, 24, 8):
+        g.process_rtl(iq[0][k * 65536:(k + 8) * 65536])
+    got = g.drain_blocks()
+    g.close()
+    wide = np.zeros((24, 32768, 2), np.float32)
+    wide[:, 1:, :] = (iq[0].reshape(24, 32768, 2).astype(np.float32) - np.float32(127.37))[:, :-1, :]
+    g2 = api.Vdl2Gpu([(0, 136_975_000, fo)], fmt="cf32", max_samples=n)
+    g2.process(wide.reshape(1, -1))
+    got2 = g2.drain_blocks()
+    g2.close()
+    assert len(got) == len(want) > 3 and got.tobytes() == got2.tobytes()
+    for a, b in zip(got, want):
+        assert a["nbrow"] == b["nbrow"] and a["nlbyte"] == b["nlbyte"] and a["sync_dump"] == b["sync_dump"]
+        assert bytes(a["data"]) == bytes(b["data"])
+    with pytest.raises(api.Vdl2Error, match="whole"):
+        g3 = api.Vdl2Gpu([(0, 136_975_000, fo)], fmt="cf32", max_samples=n)
+        g3.process_rtl(iq[0][:2000])
 
 
 @pytest.mark.gpu

@@ -61,7 +61,7 @@ class Stats(C.Structure):
 EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
            "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
-           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free"]
+           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load_library():
     lib.vdl2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.vdl2_link_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     lib.vdl2_drain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.vdl2_process_host_rtl.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.vdl2_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.vdl2_host_free.argtypes = [C.c_void_p]
     lib.vdl2_cuda_stream.restype = C.c_void_p
@@ -151,6 +152,12 @@ class Vdl2Gpu:
         nsamples = row_bytes // self.bps
         self._check(self.lib.vdl2_process_host(self.h, iq.ctypes.data_as(C.c_void_p), nsamples, row_bytes))
         return self
+
+    def process_rtl(self, cu8: np.ndarray):
+        """Raw cu8 bytes of whole 65536-byte RTL callbacks, demodulated as the reference's in_callback lays them out
+        (rtl.c:285-292), expanded on the device; the handle must have fmt="cf32" and one stream."""
+        cu8 = np.ascontiguousarray(cu8, dtype=np.uint8)
+        self._check(self.lib.vdl2_process_host_rtl(self.h, cu8.ctypes.data_as(C.c_void_p), cu8.size // 2))
 
     def process_ptr(self, host_ptr: int, nsamples: int, pitch_bytes: int):
         self._check(self.lib.vdl2_process_host(self.h, C.c_void_p(host_ptr), nsamples, pitch_bytes))

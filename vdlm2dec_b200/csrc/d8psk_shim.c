@@ -146,17 +146,10 @@ void stopVdlm2(void)
 {				/* main.c:108,244: nothing is queued on the host */
 }
 
-void vdl2shim_finish(void)
-{				/* out() ran synchronously inside vdl2shim_feed(): nothing is pending */
-}
-
-void vdl2shim_feed(const void *iq, size_t nsamples)
-{
+static void deliver(void)
+{				/* called with g_busy held, after a process call returned */
 	vdl2_frame_t *fr = g_frames;
 	int nf = 0, nb = 0;
-	pthread_mutex_lock(&g_busy);
-	if (vdl2_process_host(g_gpu, iq, nsamples, 0))
-		die("vdl2_process_host");
 	if (vdl2_drain_frames(g_gpu, fr, SHIM_QCAP, &nf, NULL, 0, &nb))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
 		die("vdl2_drain_frames");
 	for (int i = 0; i < nf; i++) {
@@ -168,16 +161,16 @@ void vdl2shim_feed(const void *iq, size_t nsamples)
 		stamp(&blk.tv, fr[i].sync_dump);
 		out(&blk, fr[i].hdata, fr[i].len);
 	}
-	pthread_mutex_unlock(&g_busy);
+}
+
+void vdl2shim_finish(void)
+{				/* out() ran synchronously inside vdl2shim_feed(): nothing is pending */
 }
 #else
-void vdl2shim_feed(const void *iq, size_t nsamples)
-{
+static void deliver(void)
+{				/* called with g_busy held, after a process call returned */
 	vdl2_block_t *out = g_blocks;
 	int n = 0;
-	pthread_mutex_lock(&g_busy);
-	if (vdl2_process_host(g_gpu, iq, nsamples, 0))
-		die("vdl2_process_host");
 	if (vdl2_drain_blocks(g_gpu, out, SHIM_QCAP, &n))
 		die("vdl2_drain_blocks");
 	for (int i = 0; i < n; i++) {
@@ -197,7 +190,6 @@ void vdl2shim_feed(const void *iq, size_t nsamples)
 		decodeVdlm2(ch);	/* takes blk, installs a fresh zeroed one (vdlm2.c:189-205) */
 	}
 	g_last_n = n;
-	pthread_mutex_unlock(&g_busy);
 }
 
 void vdl2shim_finish(void)
@@ -209,6 +201,24 @@ void vdl2shim_finish(void)
 	usleep(100000 + 500 * (unsigned)g_last_n);
 }
 #endif
+
+void vdl2shim_feed(const void *iq, size_t nsamples)
+{
+	pthread_mutex_lock(&g_busy);
+	if (vdl2_process_host(g_gpu, iq, nsamples, 0))
+		die("vdl2_process_host");
+	deliver();
+	pthread_mutex_unlock(&g_busy);
+}
+
+void vdl2shim_feed_rtl(const void *cu8, size_t nsamples)
+{
+	pthread_mutex_lock(&g_busy);
+	if (vdl2_process_host_rtl(g_gpu, cu8, nsamples))
+		die("vdl2_process_host_rtl");
+	deliver();
+	pthread_mutex_unlock(&g_busy);
+}
 
 void *rcv_thread(void *arg)
 {

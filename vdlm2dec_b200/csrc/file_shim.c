@@ -25,9 +25,11 @@
  *
  * VDL2_RTL_QUIRK=1 (cu8 only) reproduces what the reference's callback does to the stream (rtl.c:285-292: the
  * index is incremented before the store, so slot 0 of every block keeps its zero and the last sample of the
- * block is dropped; partial reads are discarded, rtl.c:278-281) by expanding to complex float on the host,
- * exactly like rtl.c; the output is then identical to the reference fed the same bytes by a dongle
- * (tests/test_replay.py).  Without it every sample of the capture is demodulated once, in order.
+ * block is dropped; partial reads are discarded, rtl.c:278-281).  The bytes still cross PCIe raw; the expansion
+ * to the reference's complex-float block layout happens on the device (vdl2_process_host_rtl).  The output is
+ * then identical to the reference fed the same bytes by a dongle (tests/test_replay.py).  VDL2_RTL_QUIRK=host
+ * expands on the host instead, exactly like rtl.c (8 B/sample upload; kept as a cross-check).  Without the
+ * variable every sample of the capture is demodulated once, in order.
  *
  * Airspy build (-DWITH_AIR, air.c instead of rtl.c): the object takes the place of air.o the same way -- initAirspy /
  * runAirspySample (vdlm2.h:106-107), SDRINRATE, SDRCLK, Fc (air.c:37-40).  main.c calls initAirspy(argv, optind, tparam)
@@ -108,7 +110,7 @@ int initFile(char *file)
 		fprintf(stderr, "Need a capture file name\n");
 		return 1;
 	}
-	g_file = fopen(file, "rb");
+	g_file = strcmp(file, "-") ? fopen(file, "rb") : stdin;	/* "-": a pipe, e.g. from rtl_sdr */
 	if (!g_file) {
 		fprintf(stderr, "Failed to open capture %s\n", file);
 		return 1;
@@ -139,12 +141,15 @@ int initFile(char *file)
 	}
 	if (getenv("VDL2_FILE_BATCH") && atol(getenv("VDL2_FILE_BATCH")) > 0)
 		g_batch = (size_t) atol(getenv("VDL2_FILE_BATCH"));
-	g_quirk = getenv("VDL2_RTL_QUIRK") && atoi(getenv("VDL2_RTL_QUIRK")) && g_format == VDL2_FMT_CU8;
+	const char *q = getenv("VDL2_RTL_QUIRK");
+	g_quirk = 0;
+	if (q && g_format == VDL2_FMT_CU8)
+		g_quirk = !strcasecmp(q, "host") ? 2 : (atoi(q) ? 1 : 0);	/* 1: expanded on the device, 2: on the host */
 	if (g_quirk)		/* whole callbacks only */
 		g_batch = (g_batch + RTLINBUFSZ / 2 - 1) / (RTLINBUFSZ / 2) * (RTLINBUFSZ / 2);
 	if (verbose > 1)
 		fprintf(stderr, "Replaying %s: format %d, %u samples/s, %zu samples per launch%s\n", file, g_format, SDRINRATE, g_batch,
-			g_quirk ? ", rtl.c block indexing" : "");
+			g_quirk == 1 ? ", rtl.c block indexing (on the device)" : g_quirk ? ", rtl.c block indexing (on the host)" : "");
 	return 0;
 }
 
@@ -203,7 +208,7 @@ int runFileSample(void)
 			fprintf(stderr, "vdl2gpu replay: %s\n", vdl2_last_error(NULL));
 			exit(1);
 		}
-	if (g_quirk && vdl2_host_alloc(g_batch * 8, (void **)&wide)) {
+	if (g_quirk == 2 && vdl2_host_alloc(g_batch * 8, (void **)&wide)) {
 		fprintf(stderr, "vdl2gpu replay: %s\n", vdl2_last_error(NULL));
 		exit(1);
 	}
@@ -219,7 +224,9 @@ int runFileSample(void)
 		sem_wait(&g_full);
 		const size_t n = g_slot[k].nsamples;
 		if (n) {
-			if (g_quirk) {
+			if (g_quirk == 1)
+				vdl2shim_feed_rtl(g_slot[k].raw, n);
+			else if (g_quirk) {
 				expand_like_rtl(g_slot[k].raw, wide, n);
 				vdl2shim_feed(wide, n);
 			} else
@@ -238,8 +245,12 @@ int runFileSample(void)
 		fprintf(stderr, "Replayed %llu samples in %.4f s (%.1f Msamples/s per channel, %d channels)\n", total, dt,
 			dt > 0 ? 1e-6 * (double)total / dt : 0.0, vdl2shim_nch());
 	}
-	fclose(g_file);
+	if (g_file != stdin)
+		fclose(g_file);
 	g_file = NULL;
+	for (int k = 0; k < 2; k++)
+		vdl2_host_free(g_slot[k].raw);
+	vdl2_host_free(wide);
 	return 0;
 }
 

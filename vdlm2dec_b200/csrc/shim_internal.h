@@ -12,6 +12,9 @@ void vdl2shim_open(unsigned fs, unsigned sdrclk, int format, size_t max_samples)
 /* demodulate nsamples samples of the stream (host memory, format of vdl2shim_open) and deliver what completed:
    blocks to decodeVdlm2() (vdlm2.c:189-205), or with -DVDL2_SHIM_LINK frames to out() (vdlm2.h:134) */
 void vdl2shim_feed(const void *iq, size_t nsamples);
+/* same for raw cu8 bytes of whole 65536-byte RTL callbacks, demodulated as the reference's in_callback lays them out
+   (rtl.c:285-292; expanded on the device, vdl2_process_host_rtl); the handle must have been opened with VDL2_FMT_CF32 */
+void vdl2shim_feed_rtl(const void *cu8, size_t nsamples);
 /* end of input: returns once what vdl2shim_feed() handed over has had time to reach out() */
 void vdl2shim_finish(void);
 #endif

@@ -86,6 +86,8 @@ struct vdl2gpu {
 	int lcap_blocks, lcap_frames;
 	cudaEvent_t lev0, lev1;
 	bool lev_valid, link_ready;
+	uint8_t *d_raw;		/* raw cu8 bytes of one vdl2_process_host_rtl() call, grown on demand */
+	size_t raw_cap;
 };
 
 static int fail(vdl2gpu * h, const char *fmt, ...)
@@ -567,6 +569,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_tap_syncs);
 	cudaFree(h->d_tap_syms);
 	cudaFree(h->d_stage);
+	cudaFree(h->d_raw);
 	cudaFree(h->d_lblocks);
 	cudaFree(h->d_frames);
 	cudaFree(h->d_lstats);
@@ -719,6 +722,56 @@ extern "C" int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples,
 	if (nsamples)
 		CK(h, cudaMemcpy2DAsync(h->d_stage + h->carry * bps, h->stage_pitch, iq, h->nstreams > 1 ? pitch_bytes : nsamples * bps,
 					nsamples * bps, h->nstreams, cudaMemcpyHostToDevice, h->stream));
+	if (run_staged(h, h->carry + nsamples))
+		return 1;
+	CK(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+/* rtl.c:285-292 on the device: out[k] of every 32768-sample block = 0 for k == 0, else (u8 - 127.37f) of sample k - 1.
+   10 bytes of HBM traffic per sample, a few microseconds per launch next to the demodulator. */
+#define RTL_BLOCK 32768u
+__global__ void vdl2_expand_rtl_kernel(const uchar2 * __restrict__ raw, float2 * __restrict__ out, size_t n)
+{
+	for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x) {
+		float2 v = make_float2(0.0f, 0.0f);
+		if ((unsigned)(k & (RTL_BLOCK - 1)) != 0u) {
+			const uchar2 u = raw[k - 1];
+			v.x = __fsub_rn((float)u.x, 127.37f);	/* (float)x - (float)127.37, rtl.c:287-289 */
+			v.y = __fsub_rn((float)u.y, 127.37f);
+		}
+		out[k] = v;
+	}
+}
+
+extern "C" int vdl2_process_host_rtl(vdl2gpu_t * h, const void *cu8, size_t nsamples)
+{
+	if (!h || !cu8)
+		return fail(h, "vdl2_process_host_rtl: null argument");
+	if (h->cfg.format != VDL2_FMT_CF32 || h->nstreams != 1)
+		return fail(h, "vdl2_process_host_rtl: needs a handle with format VDL2_FMT_CF32 and one stream");
+	if (nsamples % RTL_BLOCK)
+		return fail(h, "vdl2_process_host_rtl: %zu samples are not whole %u-sample callbacks", nsamples, RTL_BLOCK);
+	CK(h, cudaSetDevice(h->cfg.device));
+	const size_t bps = h->bytes_per_sample;	/* 8: the staging buffer holds complex float */
+	if ((h->carry + nsamples) * bps > h->stage_pitch)
+		return fail(h, "vdl2_process_host_rtl: %zu samples exceed max_samples of the handle", nsamples);
+	h->st.samples_in += nsamples;
+	if (nsamples) {
+		if (2 * nsamples > h->raw_cap) {
+			CK(h, cudaStreamSynchronize(h->stream));
+			cudaFree(h->d_raw);
+			h->d_raw = NULL;
+			h->raw_cap = 0;
+			CK(h, cudaMalloc(&h->d_raw, 2 * nsamples));
+			h->raw_cap = 2 * nsamples;
+		}
+		CK(h, cudaMemcpyAsync(h->d_raw, cu8, 2 * nsamples, cudaMemcpyHostToDevice, h->stream));
+		const int threads = 256;
+		const int blocks = (int)std::min < size_t > ((nsamples + threads - 1) / threads, (size_t) h->st.n_sm * 8);
+		vdl2_expand_rtl_kernel <<< blocks, threads, 0, h->stream >>> ((const uchar2 *)h->d_raw, (float2 *) (h->d_stage + h->carry * bps), nsamples);
+		CK(h, cudaGetLastError());
+	}
 	if (run_staged(h, h->carry + nsamples))
 		return 1;
 	CK(h, cudaStreamSynchronize(h->stream));
