@@ -137,6 +137,19 @@ def test_replay_host_logic_formats_rate_and_errors(tmp_path):
         assert p.returncode != 0 and msg in p.stderr and "Unable to init input" in p.stderr  # main.c:209-213
 
 
+@needs_host
+def test_replay_host_logic_capture_from_a_pipe(tmp_path):
+    """`-r -` reads standard input (e.g. from rtl_sdr): same messages as replaying the file."""
+    fos = _fos(["136.975"])
+    cap, nb = _capture(tmp_path, fos, nblk=30)
+    want = _messages(_replay(HOSTCHECK_BIN, cap, ["136.975"], VDL2_FILE_BATCH=200_000)[0])
+    with open(cap, "rb") as f:
+        p = subprocess.run([HOSTCHECK_BIN, *ALL, "-v", "-r", "-", "136.975"], stdin=f, capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, VDL2_FILE_BATCH="200000"))
+    assert p.returncode == 1 and f"Replayed {30 * 32768} samples" in p.stderr
+    assert _messages(p.stdout) == want and len(want) > 5
+
+
 def test_centre_frequency_rule_matches_rtl_c(tmp_path):
     """centre_for() in file_shim.c against the rule of rtl.c:123-160 restated here (first Fc from max+50 kHz downwards,
     1 Hz steps, with every channel between 50 kHz and fs/2-50 kHz away and Fc not the midpoint of two neighbours)."""
