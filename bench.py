@@ -165,14 +165,18 @@ def run_reference(args, rank, world):
     vals = []
     kind = desc = None
     threads = os.cpu_count() or 1
+    walls = []
     for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         v, threads, kind, desc = cpu_throughput(iq, fos, target_cpu_seconds=1.0 * threads)  # ~1 s wall per step
         if s >= args.warmup:
             vals.append(v)
+            walls.append(time.perf_counter() - t0)
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls),  # one step = one bounded sample (config.sample), not the GPU arm's step
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.channels} ch/GPU x {args.samples} samples, 2 Msps cu8 IQ, 1 ch/stream (BASELINE config 3); "
                                f"CPU arm runs a bounded sample of it", "sample": desc},
