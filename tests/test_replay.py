@@ -150,6 +150,29 @@ def test_replay_host_logic_capture_from_a_pipe(tmp_path):
     assert _messages(p.stdout) == want and len(want) > 5
 
 
+@needs_host
+def test_replay_host_logic_interrupt_does_not_hang(tmp_path):
+    """Ctrl-C: main.c's handler calls exit() on the main thread, which in the replay build is the thread that holds the
+    shim's busy lock while it feeds the GPU; the at-exit quiesce must not wait for itself."""
+    import signal
+    import time
+    fos = _fos(["136.975", "136.850", "136.725"])
+    cap, nb = _capture(tmp_path, fos, nblk=200)
+    data = open(cap, "rb").read()
+    with open(cap, "ab") as f:
+        for _ in range(7):
+            f.write(data)                                   # ~2 s of work for the oracle-backed stand-in
+    p = subprocess.Popen([HOSTCHECK_BIN, "-r", cap, "136.975", "136.850", "136.725"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                         env=dict(os.environ, VDL2_FILE_BATCH=str(1 << 24)))
+    time.sleep(0.4)
+    p.send_signal(signal.SIGINT)
+    try:
+        assert p.wait(timeout=20) == 1                      # sighandler: stopVdlm2(); exit(1)  (main.c:106-110)
+    finally:
+        if p.poll() is None:
+            p.kill()
+
+
 def test_centre_frequency_rule_matches_rtl_c(tmp_path):
     """centre_for() in file_shim.c against the rule of rtl.c:123-160 restated here (first Fc from max+50 kHz downwards,
     1 Hz steps, with every channel between 50 kHz and fs/2-50 kHz away and Fc not the midpoint of two neighbours)."""

@@ -43,11 +43,13 @@ extern int nbch;		/* main.c:59 */
 static channel_t *g_ch[MAXNBCHANNELS];
 static vdl2_chan_param_t g_par[MAXNBCHANNELS];
 static vdl2gpu_t *g_gpu;
-static pthread_mutex_t g_busy = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_busy = PTHREAD_ERRORCHECK_MUTEX_INITIALIZER_NP;
 
 /* main.c:246 calls exit(1) as soon as the SDR stops, while workers may still be inside the last
    block.  Registered after the CUDA runtime's own atexit hook (so it runs before it): wait for the
-   block in flight instead of tearing the context down under it. */
+   block in flight instead of tearing the context down under it.  The mutex is error-checking because
+   main.c's signal handler (main.c:106-110) calls exit() on the main thread, which in the replay build is
+   the very thread that feeds the GPU: it must not wait for itself (EDEADLK instead of a hang on Ctrl-C). */
 static void quiesce(void)
 {
 	pthread_mutex_lock(&g_busy);
