@@ -19,6 +19,10 @@ GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu")
 AIR_CPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_cpu")   # air.c + fake libairspy
 AIR_GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_gpu")
 LINK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_gpu_link")   # shim also replaces vdlm2.o + rs.o (row f1)
+# CPU-tier stand-ins: the same shim objects linked against an oracle-backed fake libvdl2gpu (oracle/ref/fake/fake_vdl2gpu.c, test
+# infrastructure): checks the shim's HOST logic (registration, Bar1/Bar2 lock-step, hand-off to decodeVdlm2) where there is no GPU
+HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_hostcheck")
+AIR_HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_hostcheck")
 ALL = ("-G", "-E", "-U")  # print ground, empty and undecoded frames too
 needs_bins = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(GPU_BIN)), reason="drop-in binaries not built")
 
@@ -93,6 +97,24 @@ def test_cpu_binary_decodes_synthetic_capture(tmp_path):
     out, err = _run(CPU_BIN, cap, ["136.975"], extra=ALL)
     assert "Fc=137025000" in err  # rtl.c:123-160 picks Fc for the single channel
     assert len(_messages(out)) == nb > 5
+
+
+@pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(HOSTCHECK_BIN)), reason="drop-in host-check binary not built")
+@pytest.mark.parametrize("freqs", [["136.975"], ["136.725", "136.975", "136.825"]])
+def test_dropin_shim_host_logic(tmp_path, freqs):
+    """The shim object itself (d8psk_gpu.o, as shipped) behind the unmodified rtl.c, with the library calls answered by the
+    oracle: the thread registration, the two-barrier lock-step with in_callback and the hand-off through decodeVdlm2 give the
+    all-reference binary's text (one channel: identical; several: the oracle's count, see the race note below)."""
+    fmax = max(float(f) for f in freqs)
+    fos = [int(round((float(f) - fmax) * 1e6)) - 50_000 for f in freqs]
+    cap, nb = _capture(tmp_path, fos, nblk=40, seed=4, acars=True)
+    a = _messages(_run(CPU_BIN, cap, freqs, extra=ALL)[0])
+    b = _messages(_run(HOSTCHECK_BIN, cap, freqs, extra=ALL)[0])
+    assert len(b) == _expected_blocks(cap, fos) > 5
+    if len(freqs) == 1:
+        assert a == b
+    else:
+        assert len(set(a) & set(b)) >= len(b) // 2
 
 
 @pytest.mark.gpu
@@ -206,6 +228,16 @@ def test_air_cpu_binary_decodes_synthetic_capture(tmp_path, fs):
     out, err = _air_run(AIR_CPU_BIN, cap, ["136.975"], fs)
     assert "fakeairspy: Fc=" in err
     assert len(_messages(out)) == _air_expected(cap, fos, fs) > 5  # every burst the oracle completes is printed
+
+
+@pytest.mark.skipif(not (os.path.exists(AIR_CPU_BIN) and os.path.exists(AIR_HOSTCHECK_BIN)), reason="Airspy drop-in host-check binary not built")
+@pytest.mark.parametrize("fs", [6_000_000, 5_000_000])
+def test_air_dropin_shim_host_logic(tmp_path, fs):
+    """Same for the -DWITH_AIR build of the shim object behind the unmodified air.c (float Cbuff of real samples)."""
+    cap, fos = _air_capture(tmp_path, fs=fs, nblk=96)
+    a = _messages(_air_run(AIR_CPU_BIN, cap, ["136.975"], fs)[0])
+    b = _messages(_air_run(AIR_HOSTCHECK_BIN, cap, ["136.975"], fs)[0])
+    assert len(b) == _air_expected(cap, fos, fs) > 5 and a == b
 
 
 @pytest.mark.gpu
