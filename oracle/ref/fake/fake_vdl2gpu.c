@@ -12,6 +12,7 @@
 #include <string.h>
 #include "vdl2gpu.h"
 #include "../../orc_api.h"
+#include "../../orc_link_api.h"
 
 struct vdl2gpu {
 	vdl2_config_t cfg;
@@ -90,6 +91,27 @@ int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out)
 	}
 	qsort(out, n, sizeof *out, by_trigger);
 	*n_out = n;
+	return 0;
+}
+
+int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int *n_frames, vdl2_block_t * blocks, int max_blocks,
+		      int *n_blocks)
+{				/* the completed blocks, oldest trigger first, through the block pipeline oracle (vdlm2.c:84-161) */
+	static vdl2_block_t own[4096];
+	vdl2_block_t *b = blocks ? blocks : own;
+	int nb = 0;
+	*n_frames = 0;
+	if (vdl2_drain_blocks(h, b, blocks ? max_blocks : 4096, &nb))
+		return 1;
+	if (n_blocks)
+		*n_blocks = nb;
+	if (nb == 0)
+		return 0;
+	if (orc_link_decode((const orc_block *)b, nb, (orc_frame *) frames, max_frames, n_frames, NULL, NULL))	/* same 2048-byte layout */
+		return 1;
+	if (!blocks)
+		for (int i = 0; i < *n_frames; i++)
+			frames[i].block = -1;
 	return 0;
 }
 

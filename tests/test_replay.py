@@ -29,6 +29,8 @@ FILE_LINK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_gpu_link")  
 HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_hostcheck")  # oracle-backed stand-in, CPU tier only
 AIR_FILE_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_file_gpu")        # -DWITH_AIR: takes the place of air.o
 AIR_HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_air_file_hostcheck")
+LINK_HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_link_hostcheck")            # rtl.c protocol, -DVDL2_SHIM_LINK
+FILE_LINK_HOSTCHECK_BIN = os.path.join(ROOT, "oracle", "_ref", "vdlm2dec_file_link_hostcheck")  # replay, -DVDL2_SHIM_LINK
 needs_host = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(HOSTCHECK_BIN)), reason="replay host-check binary not built")
 needs_file = pytest.mark.skipif(not (os.path.exists(CPU_BIN) and os.path.exists(FILE_BIN) and os.path.exists(FILE_LINK_BIN)),
                                 reason="replay binaries not built")
@@ -135,6 +137,26 @@ def test_replay_host_logic_formats_rate_and_errors(tmp_path):
                       (["-r", anon, "136.975", "135.000"], "Frequencies too far apart")):
         p = subprocess.run([HOSTCHECK_BIN, *args], capture_output=True, text=True, timeout=60)
         assert p.returncode != 0 and msg in p.stderr and "Unable to init input" in p.stderr  # main.c:209-213
+
+
+@needs_host
+@pytest.mark.skipif(not (os.path.exists(LINK_HOSTCHECK_BIN) and os.path.exists(FILE_LINK_HOSTCHECK_BIN)), reason="link host-check binaries not built")
+def test_link_variant_host_logic(tmp_path):
+    """-DVDL2_SHIM_LINK objects (no vdlm2.o / rs.o: frames go straight to out() with a msgblk_t the shim fills in): same text
+    and -J JSON as the objects that hand blocks to the reference's blk_thread, behind rtl.c and in the replay build, and in the
+    replay build with capture-time stamps the output is byte-identical."""
+    from tests.test_dropin import HOSTCHECK_BIN as RTL_HOSTCHECK_BIN
+    freqs = ["136.975", "136.850"]
+    cap, nb = _capture(tmp_path, _fos(freqs), nblk=40, seed=7, acars=True)
+    a = _run(RTL_HOSTCHECK_BIN, cap, freqs, extra=ALL)[0]
+    b = _run(LINK_HOSTCHECK_BIN, cap, freqs, extra=ALL)[0]
+    assert _messages(a) == _messages(b) and len(_messages(a)) > 5
+    t0 = dict(VDL2_FILE_T0=1577836800, VDL2_FILE_BATCH=300_000)
+    for extra in (ALL, ("-J",)):
+        c = _replay(HOSTCHECK_BIN, cap, freqs, extra=extra, **t0)[0]
+        d = _replay(FILE_LINK_HOSTCHECK_BIN, cap, freqs, extra=extra, **t0)[0]
+        assert sorted(c.split("\n[#")) == sorted(d.split("\n[#")) and len(c) > 1000
+    assert '"text":"HELLO VDL2 NUMBER 0' in d
 
 
 @needs_host
