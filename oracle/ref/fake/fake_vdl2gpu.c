@@ -26,6 +26,7 @@ int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, vdl2
 {
 	if (cfg->nch > 8 || cfg->ch_per_stream != cfg->nch)
 		return 1;
+	fprintf(stderr, "fake_vdl2gpu: TEST STAND-IN answering from the CPU oracle -- not libvdl2gpu.so, not a product path\n");
 	vdl2gpu_t *h = calloc(1, sizeof *h);
 	h->cfg = *cfg;
 	for (int c = 0; c < cfg->nch; c++)
