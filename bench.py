@@ -187,6 +187,26 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(local_rank):
+    """N > 1 only: confine this rank's host threads to the CPUs NVML reports as nearest to its GPU while the pinned e2e
+    buffer is allocated and fed, so that its pages sit on the GPU's NUMA node (8 ranks x 50 GB/s of H2D is more than one
+    socket's memory should serve across the inter-socket link).  Returns the previous affinity (to restore) or None."""
+    try:
+        import pynvml
+        import torch
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        if not os.sched_getaffinity(0):
+            os.sched_setaffinity(0, old)
+            return None
+        return old
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, local_rank, world):
     import numpy as np
@@ -277,6 +297,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- end to end through the C ABI with pinned host buffers (H2D + drain inside the timed region)
     e2e = None
     if not args.no_e2e:
+        old_affinity = bind_near_gpu(local_rank) if world > 1 else None
         hx = torch.empty((nstreams, 2 * ns), dtype=torch.uint8, pin_memory=True)
         hx.copy_(x)
         torch.cuda.synchronize()
@@ -295,8 +316,11 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": nch * ns * nrep * world / float(tt.item()) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep}
+               "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep,
+               "host_numa_bound": old_affinity is not None}
         del hx
+        if old_affinity is not None:
+            os.sched_setaffinity(0, old_affinity)
 
     # ---- block pipeline behind the demodulator: the blocks of one step through
     #      vdl2_link_kernel (RS + HDLC + FCS), next to the reference's blk_thread path on one host core
