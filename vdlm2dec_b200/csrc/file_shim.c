@@ -254,6 +254,30 @@ int runFileSample(void)
 	return 0;
 }
 
+/* The frequency list both front ends of the reference accept (rtl.c:218-237, air.c:84-110): MHz as decimal text, at most
+   MAXNBCHANNELS, values outside the aeronautical band skipped with a warning; channel numbers follow the order given.
+   Fills param[].chn / .Fr and freq[] (Hz, same order), sets nbch; returns 0 or the reference's error (message printed). */
+static int channel_list(char **argv, int first, thread_param_t * param, unsigned int *freq)
+{
+	nbch = 0;
+	for (int i = first; argv[i] != NULL && nbch < MAXNBCHANNELS; i++) {
+		const unsigned int hz = (int)(1000000 * atof(argv[i]));
+		if (hz < 118000000 || hz > 138000000) {
+			fprintf(stderr, "WARNING: Invalid frequency %d\n", hz);
+			continue;
+		}
+		freq[nbch] = hz;
+		param[nbch].chn = nbch;
+		param[nbch].Fr = hz;
+		nbch++;
+	}
+	if (nbch == 0) {
+		fprintf(stderr, "Need a least one frequency\n");
+		return 1;
+	}
+	return 0;
+}
+
 #ifdef WITH_AIR
 /* ---- the air.o seam, so that the unmodified main.c drives the replay ---- */
 
@@ -285,27 +309,14 @@ static unsigned int centre_for_real(unsigned int fmin, unsigned int fmax)
 
 int initAirspy(char **argv, int optind, thread_param_t * param)
 {				/* main.c:205, after the options: argv[optind...] are the frequencies (air.c:84-110) */
-	unsigned int fmin = 140000000, fmax = 0;
-	char *a;
-	nbch = 0;
-	while ((a = argv[optind]) && nbch < MAXNBCHANNELS) {
-		const unsigned int f = (int)(1000000 * atof(a));
-		optind++;
-		if (f < 118000000 || f > 138000000) {
-			fprintf(stderr, "WARNING: Invalid frequency %d\n", f);
-			continue;
-		}
-		param[nbch].chn = nbch;
-		param[nbch].Fr = f;
-		if (f < fmin)
-			fmin = f;
-		if (f > fmax)
-			fmax = f;
-		nbch++;
-	}
-	if (nbch == 0) {
-		fprintf(stderr, "Need a least one frequency\n");
+	unsigned int freq[MAXNBCHANNELS], fmin = 140000000, fmax = 0;
+	if (channel_list(argv, optind, param, freq))
 		return 1;
+	for (int n = 0; n < nbch; n++) {
+		if (freq[n] < fmin)
+			fmin = freq[n];
+		if (freq[n] > fmax)
+			fmax = freq[n];
 	}
 	if (!getenv("VDL2_FILE")) {
 		fprintf(stderr, "Name the capture to replay in VDL2_FILE\n");
@@ -375,28 +386,13 @@ static unsigned int centre_for(unsigned int *fd, int n)
 int initRtl(char **argv, int optind, thread_param_t * param)
 {				/* main.c:141-143 calls this at "-r": argv[optind] is the capture, the rest the frequencies */
 	unsigned int fd[MAXNBCHANNELS];
-	char *a;
 	if (argv[optind] == NULL) {
 		fprintf(stderr, "Need a capture file name after -r\n");
 		exit(1);
 	}
-	char *file = argv[optind++];
-	nbch = 0;
-	while ((a = argv[optind]) && nbch < MAXNBCHANNELS) {	/* rtl.c:218-231 */
-		fd[nbch] = (int)(1000000 * atof(a));
-		optind++;
-		if (fd[nbch] < 118000000 || fd[nbch] > 138000000) {
-			fprintf(stderr, "WARNING: Invalid frequency %d\n", fd[nbch]);
-			continue;
-		}
-		param[nbch].chn = nbch;
-		param[nbch].Fr = fd[nbch];
-		nbch++;
-	}
-	if (nbch == 0) {
-		fprintf(stderr, "Need a least one frequency\n");
+	char *file = argv[optind];
+	if (channel_list(argv, optind + 1, param, fd))
 		return 1;
-	}
 	if (initFile(file))	/* before the centre: VDL2_FILE_RATE changes the usable span */
 		return 1;
 	if (getenv("VDL2_FILE_FC"))	/* the capture was taken at a known centre */
