@@ -208,3 +208,43 @@ def time_cu8(kind: str, iq: np.ndarray, reps: int, Fr=136_975_000, Fo=-50_000, f
     lib = load(kind)
     iq = np.ascontiguousarray(iq)
     return float(lib.orc_time_cu8(Fr, Fo, fs, sdrclk, iq.ctypes.data_as(C.c_void_p), iq.size // 2, reps))
+
+
+# ---- row f4 (oracle only so far): the fields out() / outacars() derive from a frame before formatting (orc_avlc_api.h)
+AVLC_DT = np.dtype([("faddr", "<u4"), ("taddr", "<u4"), ("fromair", "u1"), ("rep", "u1"), ("gnd", "u1"), ("lc", "u1"), ("kind", "u1"),
+                    ("mode", "u1"), ("ack", "u1"), ("bid", "u1"), ("bs", "u1"), ("be", "u1"), ("label", "u1", (2,)), ("reg", "u1", (7,)),
+                    ("nno", "u1"), ("nfid", "u1"), ("no", "u1", (4,)), ("fid", "u1", (6,)), ("pad", "u1"),
+                    ("txt_off", "<u2"), ("txt_len", "<u2"), ("info_off", "<u2"), ("info_len", "<u2")])
+assert AVLC_DT.itemsize == 48
+AVLC_KINDS = ("empty", "xid", "acars", "acars_badcrc", "other")
+_AVLC = {}
+
+
+def _avlc_lib(kind: str):
+    if kind not in _AVLC:
+        path = os.path.join(HERE, "libvdl2avlcport.so") if kind == "port" else os.path.join(HERE, "_ref", "libvdl2outref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"oracle library {path} missing (run `make -C oracle`)")
+        lib = C.CDLL(path)
+        if kind == "port":
+            lib.orc_avlc_extract.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        else:
+            lib.orc_out_json.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_char_p, C.c_int]
+        _AVLC[kind] = lib
+    return _AVLC[kind]
+
+
+def avlc_extract(hdata: bytes) -> np.ndarray:
+    """Port: the binary record of one frame (hdata including both flags, as handed to out(); vdlm2.h:134)."""
+    rec = np.zeros(1, AVLC_DT)
+    buf = (C.c_uint8 * (len(hdata) + 64)).from_buffer_copy(bytes(hdata) + bytes(64))
+    _avlc_lib("port").orc_avlc_extract(buf, len(hdata), rec.ctypes.data_as(C.c_void_p))
+    return rec[0]
+
+
+def out_json(hdata: bytes, chn: int = 0, Fr: int = 136_975_000, ppm: float = 0.0, t: float = 0.0) -> str:
+    """Reference: the JSON line its out() prints for this frame with -J -G -E ('' when it prints none)."""
+    buf = C.create_string_buffer(60000)
+    src = (C.c_uint8 * len(hdata)).from_buffer_copy(bytes(hdata))
+    n = _avlc_lib("ref").orc_out_json(src, len(hdata), chn, Fr, C.c_float(ppm), C.c_double(t), buf, len(buf))
+    return buf.raw[:n].decode("latin-1")
