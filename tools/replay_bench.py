@@ -39,7 +39,8 @@ if __name__ == "__main__":
                 ("file replay, raw cu8, block pipeline on device", "vdlm2dec_file_gpu_link", {}),
                 ("file replay, raw cu8, block pipeline on device, 2^24-sample launches", "vdlm2dec_file_gpu_link", {"VDL2_FILE_BATCH": str(1 << 24)}),
                 ("file replay, raw cu8, block pipeline on device, 2^20-sample launches", "vdlm2dec_file_gpu_link", {"VDL2_FILE_BATCH": str(1 << 20)}),
-                ("file replay, rtl.c indexing (host expansion to complex float)", "vdlm2dec_file_gpu_link", {"VDL2_RTL_QUIRK": "1"})]
+                ("file replay, rtl.c indexing (raw upload, expanded on the device)", "vdlm2dec_file_gpu_link", {"VDL2_RTL_QUIRK": "1"}),
+                ("file replay, rtl.c indexing (host expansion to complex float)", "vdlm2dec_file_gpu_link", {"VDL2_RTL_QUIRK": "host"})]
         for nch in (1, 8):
             for name, binary, env in runs:
                 b = os.path.join(R, binary)
