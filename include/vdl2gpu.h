@@ -204,6 +204,38 @@ int vdl2_host_free(void *p);
    of 32768-sample callbacks.  Output is bit-identical to the reference fed the same bytes. */
 int vdl2_process_host_rtl(vdl2gpu_t * h, const void *cu8, size_t nsamples);
 
+/* ---- frame fields: what the reference's out() (out.c:517-570) and outacars()
+   (outacars.c:214-290) derive from the bytes of a frame BEFORE they format text or JSON -- addresses through icaoaddr()
+   (out.c:426-435), direction, command/response, on-ground bit, link control byte, payload class, and for ACARS the CRC
+   verdict, the parity-stripped header fields and the extent of the message text.  Formatting stays on the host. ---- */
+enum vdl2_avlc_kind {
+	VDL2_AVLC_EMPTY = 0,		/* l <= 13: no information field (out.c:530) */
+	VDL2_AVLC_XID = 1,		/* hdata[10] == 0x82 (out.c:562) */
+	VDL2_AVLC_ACARS = 2,		/* ff ff 01 header, ACARS CRC good (out.c:566, outacars.c:222-230) */
+	VDL2_AVLC_ACARS_BADCRC = 3,
+	VDL2_AVLC_OTHER = 4		/* anything else with l > 13 ("unknown data", out.c:570) */
+};
+
+typedef struct {
+	uint32_t faddr, taddr;	/* icaoaddr(&hdata[5]), icaoaddr(&hdata[1]): 3-bit type << 24 | 24-bit address */
+	uint8_t fromair;	/* (faddr >> 24) == 1 */
+	uint8_t rep;		/* 1 = response, 0 = command */
+	uint8_t gnd;		/* aircraft on ground */
+	uint8_t lc;		/* link control byte hdata[9] (outlinkctrl, out.c:484-504) */
+	uint8_t kind;		/* enum vdl2_avlc_kind */
+	uint8_t mode, ack, bid, bs, be;	/* ACARS, parity stripped; ack 0x15 -> '!', bid 0 -> ' ' (outacars.c:243-261) */
+	uint8_t label[2];	/* label[1] 0x7f -> 'd' */
+	uint8_t reg[7];		/* registration as sent (fixreg()'s formatting stays on the host) */
+	uint8_t nno, nfid;	/* characters in no[] / fid[] */
+	uint8_t no[4], fid[6];
+	uint8_t pad;
+	uint16_t txt_off, txt_len;	/* message text = hdata[txt_off .. txt_off + txt_len), each byte & 0x7f */
+	uint16_t info_off, info_len;	/* information field of any kind: hdata[10 .. l - 3) */
+} vdl2_avlc_t;			/* 48 bytes */
+
+/* frames (as returned by vdl2_link_decode / vdl2_drain_frames) -> one record per frame, same order */
+int vdl2_avlc_extract(vdl2gpu_t * h, const vdl2_frame_t * frames, int nframes, vdl2_avlc_t * recs);
+
 int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
 /* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */
 void *vdl2_cuda_stream(vdl2gpu_t * h);

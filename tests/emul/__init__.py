@@ -13,7 +13,34 @@ LIB = os.path.join(HERE, "libvdl2emul.so")
 _lib = None
 
 
+AVLC_LIB = os.path.join(HERE, "libvdl2avlcemul.so")
+_avlc = None
+
+
+def build_avlc():
+    src = os.path.join(HERE, "avlc_host.cpp")
+    hdr = os.path.join(ROOT, "vdlm2dec_b200", "csrc", "vdl2_avlc.cuh")
+    if os.path.exists(AVLC_LIB) and all(os.path.getmtime(AVLC_LIB) >= os.path.getmtime(d) for d in (src, hdr)):
+        return AVLC_LIB
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", f"-I{os.path.join(ROOT, 'vdlm2dec_b200', 'csrc')}",
+                    "-o", AVLC_LIB, src], check=True)
+    return AVLC_LIB
+
+
+def avlc(frames: np.ndarray) -> np.ndarray:
+    """The row-f4 kernel's per-frame walk (vdl2_avlc.cuh) on the host: frames (FRAME_DT) -> 48-byte records."""
+    global _avlc
+    from oracle.pyoracle import AVLC_DT, FRAME_DT
+    if _avlc is None:
+        _avlc = C.CDLL(build_avlc())
+    frames = np.ascontiguousarray(frames, dtype=FRAME_DT)
+    recs = np.zeros(len(frames), AVLC_DT)
+    _avlc.emul_avlc(frames.ctypes.data_as(C.c_void_p), len(frames), recs.ctypes.data_as(C.c_void_p))
+    return recs
+
+
 def build():
+    build_avlc()
     src = os.path.join(HERE, "emul_main.cpp")
     deps = [src, os.path.join(HERE, "vdl2_emul.h")] + [os.path.join(ROOT, "vdlm2dec_b200", "csrc", f)
                                                         for f in ("vdl2_demod.cuh", "vdl2_common.h", "vdl2_tables.h")]

@@ -45,6 +45,7 @@ def test_struct_layouts_match_header():
     from oracle import pyoracle
     assert api.FRAME_DT.itemsize == 2048 and api.FRAME_DT.fields["hdata"][1] == 32 and api.FRAME_DT == pyoracle.FRAME_DT
     assert api.BLKSTAT_DT.itemsize == 16 and api.BLKSTAT_DT == pyoracle.BLKSTAT_DT
+    assert api.AVLC_DT.itemsize == 48 and api.AVLC_DT == pyoracle.AVLC_DT and api.AVLC_DT.fields["txt_off"][1] == 40  # vdl2_avlc_t (row f4)
     hdr = open(os.path.join(ROOT, "include", "vdl2gpu.h")).read()
     assert "uint8_t hdata[2016];" in hdr and "} vdl2_frame_t;" in hdr and "#define VDL2_ABI_VERSION 3" in hdr
 

@@ -39,6 +39,12 @@ FRAME_DT = np.dtype([("block", "<i4"), ("len", "<i4"), ("chn", "<i4"), ("Fr", "<
                      ("sync_dump", "<i8"), ("hdata", "u1", (2016,))])
 BLKSTAT_DT = np.dtype([("rs", "i1", (8,)), ("nbytes", "<i4"), ("nframes", "<i4")])
 assert FRAME_DT.itemsize == 2048 and BLKSTAT_DT.itemsize == 16
+# vdl2_avlc_t (row f4): the fields out() / outacars() derive from a frame before formatting
+AVLC_DT = np.dtype([("faddr", "<u4"), ("taddr", "<u4"), ("fromair", "u1"), ("rep", "u1"), ("gnd", "u1"), ("lc", "u1"), ("kind", "u1"),
+                    ("mode", "u1"), ("ack", "u1"), ("bid", "u1"), ("bs", "u1"), ("be", "u1"), ("label", "u1", (2,)), ("reg", "u1", (7,)),
+                    ("nno", "u1"), ("nfid", "u1"), ("no", "u1", (4,)), ("fid", "u1", (6,)), ("pad", "u1"),
+                    ("txt_off", "<u2"), ("txt_len", "<u2"), ("info_off", "<u2"), ("info_len", "<u2")])
+assert AVLC_DT.itemsize == 48
 
 
 class ChanParam(C.Structure):  # thread_param_t, vdlm2.h:49-52
@@ -61,7 +67,7 @@ class Stats(C.Structure):
 EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
            "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
-           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl"]
+           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl", "vdl2_avlc_extract"]
 
 _lib = None
 
@@ -89,6 +95,7 @@ def load_library():
     lib.vdl2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.vdl2_link_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     lib.vdl2_drain_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.vdl2_avlc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.vdl2_process_host_rtl.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.vdl2_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.vdl2_host_free.argtypes = [C.c_void_p]
@@ -189,6 +196,13 @@ class Vdl2Gpu:
                                               len(frames), C.byref(nf), stats.ctypes.data_as(C.c_void_p),
                                               rows.ctypes.data_as(C.c_void_p) if want_rows else None))
         return frames[:nf.value].copy(), stats, rows
+
+    def avlc_extract(self, frames: np.ndarray) -> np.ndarray:
+        """Row f4: one field record per frame (addresses, direction, payload class, ACARS header fields and text extent)."""
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DT)
+        recs = np.zeros(len(frames), AVLC_DT)
+        self._check(self.lib.vdl2_avlc_extract(self.h, frames.ctypes.data_as(C.c_void_p), len(frames), recs.ctypes.data_as(C.c_void_p)))
+        return recs
 
     def drain_frames(self):
         """Completed blocks -> block pipeline on the device -> (frames, blocks); frame['block'] indexes blocks."""

@@ -86,6 +86,8 @@ struct vdl2gpu {
 	int lcap_blocks, lcap_frames;
 	cudaEvent_t lev0, lev1;
 	bool lev_valid, link_ready;
+	void *d_avlc;		/* field records of one vdl2_avlc_extract() call, grown on demand */
+	int avlc_cap;
 	uint8_t *d_raw;		/* raw cu8 bytes of one vdl2_process_host_rtl() call, grown on demand */
 	size_t raw_cap;
 };
@@ -221,6 +223,10 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->row_bytes = h->row_samples * h->bytes_per_sample;
 	h->spc = 16 / h->bytes_per_sample;
 	h->ev_valid = false;
+	h->d_raw = NULL;
+	h->raw_cap = 0;
+	h->d_avlc = NULL;
+	h->avlc_cap = 0;
 	h->d_lblocks = NULL;
 	h->d_frames = NULL;
 	h->d_lstats = NULL;
@@ -570,6 +576,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_tap_syms);
 	cudaFree(h->d_stage);
 	cudaFree(h->d_raw);
+	cudaFree(h->d_avlc);
 	cudaFree(h->d_lblocks);
 	cudaFree(h->d_frames);
 	cudaFree(h->d_lstats);
@@ -1033,6 +1040,34 @@ extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_f
 	h->st.blocks_out += n;
 	if (n_blocks)
 		*n_blocks = (int)n;
+	return 0;
+}
+
+/* ---- frame fields (row f4) ---- */
+extern "C" int vdl2_avlc_extract(vdl2gpu_t * h, const vdl2_frame_t * frames, int nframes, vdl2_avlc_t * recs)
+{
+	if (!h || (nframes > 0 && (!frames || !recs)))
+		return fail(h, "vdl2_avlc_extract: null argument");
+	if (nframes <= 0)
+		return 0;
+	static_assert(sizeof(vdl2_frame_t) == sizeof(Vdl2FrameRec) && sizeof(vdl2_avlc_t) == 48, "record layouts");
+	CK(h, cudaSetDevice(h->cfg.device));
+	if (link_reserve(h, 0, nframes, false))
+		return 1;
+	if (nframes > h->avlc_cap) {
+		cudaFree(h->d_avlc);
+		h->d_avlc = NULL;
+		h->avlc_cap = 0;
+		const int cap = std::max(nframes, 256);
+		CK(h, cudaMalloc(&h->d_avlc, sizeof(vdl2_avlc_t) * (size_t) cap));
+		h->avlc_cap = cap;
+	}
+	CK(h, cudaMemcpyAsync(h->d_frames, frames, sizeof(Vdl2FrameRec) * (size_t) nframes, cudaMemcpyHostToDevice, h->stream));
+	cudaError_t e = (cudaError_t) vdl2_avlc_launch(h->d_frames, nframes, h->d_avlc, h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "frame field kernel launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaMemcpyAsync(recs, h->d_avlc, sizeof(vdl2_avlc_t) * (size_t) nframes, cudaMemcpyDeviceToHost, h->stream));
+	CK(h, cudaStreamSynchronize(h->stream));
 	return 0;
 }
 

@@ -23,6 +23,8 @@ extern "C" {
 int vdl2_link_upload_tables(void);
 int vdl2_link_launch(const Vdl2BlockRec * d_blocks, int nblocks, Vdl2FrameRec * d_frames, unsigned *d_nframes, unsigned cap,
 		     Vdl2BlkStat * d_stats, uint8_t * d_rows_after, void *stream);
+/* vdl2_avlc.cu (row f4): one 48-byte field record per frame */
+int vdl2_avlc_launch(const Vdl2FrameRec * d_frames, int nframes, void *d_recs, void *stream);
 #ifdef __cplusplus
 }
 #endif
