@@ -161,7 +161,6 @@ def test_product_walk_equals_port_on_host():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="row f4 kernel: checked on the host against the port, first GPU run still pending (DESIGN.md 8c)")
 def test_avlc_kernel_equals_port_on_gpu():
     """vdl2_avlc_extract through the C ABI: records byte for byte equal to the oracle port."""
     from vdlm2dec_b200 import api
