@@ -46,6 +46,8 @@ extern "C" {
 void orc_avlc_extract(const uint8_t * hdata, int l, orc_avlc * rec);
 /* reference: the JSON line out() prints with -J -G -E for this frame (empty string if it prints none); returns its length */
 int orc_out_json(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap);
+/* reference: the TEXT out() prints at the default verbosity with -G -E -U for this frame; returns its length */
+int orc_out_text(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap);
 #ifdef __cplusplus
 }
 #endif

@@ -230,6 +230,7 @@ def _avlc_lib(kind: str):
             lib.orc_avlc_extract.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         else:
             lib.orc_out_json.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_char_p, C.c_int]
+            lib.orc_out_text.argtypes = lib.orc_out_json.argtypes
         _AVLC[kind] = lib
     return _AVLC[kind]
 
@@ -247,4 +248,12 @@ def out_json(hdata: bytes, chn: int = 0, Fr: int = 136_975_000, ppm: float = 0.0
     buf = C.create_string_buffer(60000)
     src = (C.c_uint8 * len(hdata)).from_buffer_copy(bytes(hdata))
     n = _avlc_lib("ref").orc_out_json(src, len(hdata), chn, Fr, C.c_float(ppm), C.c_double(t), buf, len(buf))
+    return buf.raw[:n].decode("latin-1")
+
+
+def out_text(hdata: bytes, chn: int = 0, Fr: int = 136_975_000, ppm: float = 0.0, t: float = 0.0) -> str:
+    """Reference: the text its out() prints for this frame at the default verbosity with -G -E -U."""
+    buf = C.create_string_buffer(60000)
+    src = (C.c_uint8 * len(hdata)).from_buffer_copy(bytes(hdata))
+    n = _avlc_lib("ref").orc_out_text(src, len(hdata), chn, Fr, C.c_float(ppm), C.c_double(t), buf, len(buf))
     return buf.raw[:n].decode("latin-1")

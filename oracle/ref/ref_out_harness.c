@@ -25,7 +25,27 @@ unsigned int reversebits(const unsigned int bits, const int n)
 	return r;
 }
 
+static int run_out(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap);
+
 int orc_out_json(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap)
+{
+	verbose = 0;
+	jsonout = 1;
+	undecmess = 0;
+	return run_out(hdata, l, chn, Fr, ppm, t, buf, cap);
+}
+
+/* the text out() prints at the default verbosity with -G -E -U (header line, "Command/Response from <addr> (...) to <addr>",
+   link control line, payload): verbose 1 never reaches the hex dumps whose buffer the reference overruns */
+int orc_out_text(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap)
+{
+	verbose = 1;
+	jsonout = 0;
+	undecmess = 1;
+	return run_out(hdata, l, chn, Fr, ppm, t, buf, cap);
+}
+
+static int run_out(const uint8_t * hdata, int l, int chn, int Fr, float ppm, double t, char *buf, int cap)
 {
 	static unsigned char copy[65 * 249];	/* out() strips the ACARS parity bits in place (outacars.c:225) */
 	char *mem = NULL;

@@ -171,3 +171,34 @@ def test_avlc_kernel_equals_port_on_gpu():
     g.close()
     want = np.array([pyoracle.avlc_extract(f) for f in frames], dtype=pyoracle.AVLC_DT)
     assert got.tobytes() == want.tobytes()
+
+
+@needs_ref
+def test_header_fields_match_reference_text_for_every_address_type():
+    """Frames that are NOT ACARS (so no JSON): the addresses, their types, command/response, the on-ground bit and the payload
+    class of the port against the TEXT the reference's out() prints (outaddr out.c:437-470, out.c:545-551,570)."""
+    import re
+    rng = np.random.default_rng(3)
+    names = {0: "T0:%06X", 1: "Aircraft:%06X", 2: "T2:%06X", 3: "T3:%06X", 4: "GroundA:%06X", 5: "GroundD:%06X", 6: "T6:%06X"}
+    n = 0
+    for i in range(400):
+        st, dt = int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        src = synth.avlc_addr((st << 24) | int(rng.integers(0, 1 << 24)), int(rng.integers(0, 2)), True)
+        dst = synth.avlc_addr((dt << 24) | int(rng.integers(0, 1 << 24)), int(rng.integers(0, 2)), False)
+        info = bytes(rng.integers(0, 256, int(rng.integers(0, 30)), dtype=np.uint8).tobytes())
+        if info and info[0] in (0x82, 0xFF):            # XID / ACARS parsing of random bytes is not what this test is about
+            info = b"\x01" + info[1:]
+        f = _frame(dst + src + bytes([int(rng.integers(0, 256))]) + info)
+        r = pyoracle.avlc_extract(f)
+        assert r["faddr"] >> 24 == st and r["taddr"] >> 24 == dt
+        text = pyoracle.out_text(f)
+        m = re.search(r"\n(Command|Response) from (.*?)\((on ground|airborne)\) to (.*?)\n", text)
+        assert m, text
+        assert (m.group(1) == "Response") == bool(r["rep"])
+        want_from = "All " if st == 7 else names[st] % (int(r["faddr"]) & 0xFFFFFF) + " "
+        want_to = "All " if dt == 7 else names[dt] % (int(r["taddr"]) & 0xFFFFFF) + " "
+        assert m.group(2) == want_from and m.group(4) == want_to
+        assert (m.group(3) == "on ground") == bool(r["fromair"] and r["gnd"])
+        assert ("unknown data" in text) == (pyoracle.AVLC_KINDS[r["kind"]] == "other")
+        n += pyoracle.AVLC_KINDS[r["kind"]] == "empty"
+    assert n > 3
