@@ -3,8 +3,9 @@
  *
  * Owns the device buffers (per-channel state, NCO tables, block queue, tap logs, the input
  * staging ring), builds the TMA descriptor for every launch and launches the fused
- * front-end kernel.  No demodulation happens on the host; if CUDA is unavailable every
- * entry point fails (there is deliberately no CPU fallback).
+ * front-end kernel; behind it the block pipeline (vdl2_link.cu, row f1), the frame-field kernel (vdl2_avlc.cu,
+ * row f4), page-locked ingest buffers and the on-device rtl.c block expansion (row f2).  No demodulation
+ * happens on the host; if CUDA is unavailable every entry point fails (there is deliberately no CPU fallback).
  *
  * Host-side arithmetic that must equal the reference's:
  *   NCO table   d8psk.c:353-357   wf[n] = cexpf(-n * Fo' * I), Fo' rounded to float,
