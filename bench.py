@@ -197,7 +197,11 @@ def bind_near_gpu(local_rank):
         old = os.sched_getaffinity(0)
         pynvml.nvmlInit()
         uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
-        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except TypeError:  # older bindings want bytes
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
         pynvml.nvmlDeviceSetCpuAffinity(h)
         if not os.sched_getaffinity(0):
             os.sched_setaffinity(0, old)
