@@ -116,3 +116,28 @@ def test_synth_roundtrip_helpers():
     tx = synth.make_burst(np.random.default_rng(1), 200)
     assert tx.valid and tx.tx_bits.size == 25 + 8 * len(tx._byte_order())
     assert synth.scrambler_sequence(8).tolist() == [1, 1, 0, 1, 0, 0, 1, 0] or len(synth.scrambler_sequence(8)) == 8
+
+
+def test_phase2_noise_free_tail_is_the_only_place_phase_is_ill_conditioned():
+    """Found by a randomized sweep of the emulated phase-2 source against the oracle (tools/fuzz_phase2.py, 2 000 cases over Fo, amplitude,
+    noise, burst spacing, tile size and speculation mode: every case with noise inside the 1e-5 rad bar; 6 noise-free cases at
+    |Fo| = 200 kHz outside it, at most 5.9e-5 rad).  In noise-free input the last symbols of a burst are read after the transmitter stopped:
+    what is left is the -0.37 LSB residue of the cu8 conversion, 0.07 LSB after the channel filter against 45+ LSB inside the
+    burst, and the phase of a 0.07 LSB vector moves by 3e-5 rad when the filter sum differs in its last bit (the kernel sums
+    in pairs, the reference sequentially).  Pinned here: the deviation is confined to such symbols, stays below 1e-4 rad,
+    and changes nothing that leaves the demodulator (hard bits, Gray index, blocks)."""
+    n, fo = 800_000, 200_000
+    spec = synth.standard_channel(seed=1003604752, nsamples=n, Fo=fo, period=66063, payload_bytes=(14, 600),
+                                  amp=(45.505150349025584, 45.505150349025584 * 1.5), noise_sigma=0.0)
+    o = Oracle("port", Fo=fo).feed(synth.render_channel(spec, n))
+    b, _, sy, sm = emul.demod(o.dumps, 1008, want_steps=False)
+    osm = o.syms
+    assert len(sm) == len(osm) > 2000 and np.array_equal(sm["dump"], osm["dump"])
+    dev = np.minimum(np.abs(sm["D"].astype(np.float64) - osm["D"]), 2 * np.pi - np.abs(sm["D"].astype(np.float64) - osm["D"]))
+    loud = np.array([np.abs(o.dumps[int(d) - 16:int(d) + 1]).min() for d in osm["dump"]])      # weakest dump in the filter window
+    burst_level = np.median(loud)
+    off = dev >= 1e-5
+    assert 0 < off.sum() <= 4 and dev.max() < 1e-4
+    assert (loud[off] < 0.01 * burst_level).all() and (dev[loud > 0.05 * burst_level] < 1e-5).all()
+    assert np.array_equal(sm["gi"], osm["gi"]) and np.array_equal(sm["v"] > 0.5, osm["v"] > 0.5)
+    assert len(b) == len(o.blocks) and all(np.array_equal(x["data"], y["data"]) for x, y in zip(b, o.blocks))
