@@ -1,8 +1,10 @@
 """Randomized sweep of the kernel's phase-2 SOURCE (vdl2_demod.cuh through the host warp emulator, tests/emul) against the
 oracle: random Fo on the 25 kHz raster, amplitude, noise, burst spacing, tile size and speculation mode per case; blocks, trigger
 events, symbol positions, soft symbols (1e-5 rad) and hard decisions compared by tests/parity_util.compare_channel.  CPU only.
-    python tools/fuzz_phase2.py <seed> <cases>
-Round 1: 2 000 cases (seeds 11-14 x 500): 1 994 inside the bar, 6 outside -- all noise-free at |Fo| = 200 kHz, see DESIGN.md section 5."""
+    python tools/fuzz_phase2.py <seed> <cases> [lowsnr]
+Round 1: 2 000 cases (seeds 11-14 x 500): 1 994 inside the bar, 6 outside -- all noise-free at |Fo| = 200 kHz, see DESIGN.md section 5.
+`lowsnr` (amplitude 3-12 LSB in noise of sigma 6-24 LSB: marginal and false triggers): 1 400 cases (seeds 31-34 x 350), control flow
+identical everywhere, 2 single symbols at 1.01e-5 / 1.10e-5 rad (deep fades)."""
 import os
 import sys
 import time
@@ -20,7 +22,10 @@ t0 = time.time()
 for it in range(N):
     fo = int(rng.choice(fos)); seed = int(rng.integers(0, 1 << 30))
     n = 800_000
-    amp_lo = float(rng.uniform(8, 60)); sigma = float(rng.choice([0.0, 2.0, 4.0, 8.0]))
+    if len(sys.argv) > 3 and sys.argv[3] == "lowsnr":
+        amp_lo = float(rng.uniform(3, 12)); sigma = float(rng.choice([6.0, 8.0, 12.0, 16.0, 24.0]))
+    else:
+        amp_lo = float(rng.uniform(8, 60)); sigma = float(rng.choice([0.0, 2.0, 4.0, 8.0]))
     period = int(rng.integers(25_000, 80_000))
     tile = int(rng.choice([2688, 84, 84 * 3, 84 * 7, 84 * 12, 1000, 500]))
     flags = int(rng.choice([0, 0x100, 0x200]))
