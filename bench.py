@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle self-check of the timed workload")
+    ap.add_argument("--check-channels", type=int, default=8)
     return ap.parse_args()
 
 
@@ -145,26 +147,24 @@ def cpu_throughput(iq_rows, fos, target_cpu_seconds: float, threads: int | None 
 
 
 def host_workload(nrows: int, nsamples: int, seed: int):
-    """Small host-side (numpy) version of the workload for the CPU-only reference arm."""
-    import numpy as np
-    from vdlm2dec_b200 import synth
-    fos = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
-    rows = []
-    for c in range(nrows):
-        spec = synth.standard_channel(seed=seed + c, nsamples=nsamples, Fo=fos[c % len(fos)], period=int(0.4 * FS),
-                                      payload_bytes=(30, 600))
-        rows.append(synth.render_channel(spec, nsamples))
-    return np.stack(rows), [fos[c % len(fos)] for c in range(nrows)]
+    """The first `nrows` channels of the GPU arm's workload, built on the HOST by the same generator and seed
+    (vdlm2dec_b200.synth_torch.make_device_workload on the CPU device: same burst library, positions, amplitudes, Fo
+    per channel; the noise comes from the CPU generator instead of the CUDA one)."""
+    import torch
+    from vdlm2dec_b200.synth_torch import make_device_workload
+    x, fos, _nb = make_device_workload(nrows, nsamples, seed=seed, device=torch.device("cpu"), group=4)
+    return x.numpy(), fos[:nrows]
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = min(args.samples, 1 << 21)
-    iq, fos = host_workload(2, n, seed=100)
+    threads = os.cpu_count() or 1
+    ns = args.samples // 2000 * 2000
+    # one private channel per host thread, full step length (no cache-resident replay): rows 0..threads-1 of the GPU workload
+    iq, fos = host_workload(min(threads, 64), ns, seed=1000)
     vals = []
     kind = desc = None
-    threads = os.cpu_count() or 1
     walls = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -178,8 +178,10 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls),  # one step = one bounded sample (config.sample), not the GPU arm's step
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.channels} ch/GPU x {args.samples} samples, 2 Msps cu8 IQ, 1 ch/stream (BASELINE config 3); "
-                               f"CPU arm runs a bounded sample of it", "sample": desc},
+        "config": {"workload": f"{args.channels} channels/GPU x {ns} samples, 2 Msps cu8 IQ, 1 ch/stream (BASELINE config 3; "
+                               f"config 4 = the same per GPU at N=8)", "channels_per_gpu": args.channels, "samples_per_channel": ns,
+                   "sample": desc, "inputs": "channels 0.. of the GPU arm's workload (same generator, seed 1000), one per host thread, "
+                                             "each the full step length"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,6 +211,48 @@ def bind_near_gpu(local_rank):
         return old
     except Exception:
         return None
+
+
+def self_check(x, chans, fos, ns, cps, device, nchk):
+    """`nchk` channels of the timed tensor (spread over the channel range) through a fresh handle, against the CPU checker
+    (oracle/_ref = the reference's d8psk.c when present, else the port) fed the same bytes: completed blocks bit exact."""
+    import numpy as np
+    from oracle import pyoracle
+    from vdlm2dec_b200.api import Vdl2Gpu
+    kind = "port"
+    if pyoracle.available("ref"):
+        try:
+            pyoracle.load("ref")
+            kind = "ref"
+        except OSError:
+            pass
+    if kind == "port" and not pyoracle.available("port"):
+        pyoracle.build("port")
+    nstreams = x.shape[0]
+    pick = sorted({int(i * (nstreams - 1) / max(1, nchk - 1)) for i in range(nchk)})
+    sub = x[pick].contiguous()
+    sel = [c for s_ in pick for c in range(s_ * cps, (s_ + 1) * cps)]
+    g = Vdl2Gpu([chans[c] for c in sel], ch_per_stream=cps, device=device, max_samples=ns)
+    g.process_device(sub.data_ptr(), ns, sub.stride(0))
+    g.sync()
+    blocks = g.drain_blocks()
+    host = sub.cpu().numpy()
+    nblk, bad = 0, []
+    for i, c in enumerate(sel):
+        chn, Fr, Fo = chans[c]
+        o = pyoracle.Oracle(kind, chn=chn, Fr=Fr, Fo=Fo, taps=pyoracle.TAP_BLOCKS).feed(host[i // cps])
+        want = o.blocks
+        want = want[want["end_dump"] < ns // 2000 * 84]
+        got = blocks[blocks["chn"] == chn]
+        same = len(want) == len(got) and all(
+            a["sync_dump"] == b["sync_dump"] and a["end_dump"] == b["end_dump"] and a["nbrow"] == b["nbrow"] and a["nlbyte"] == b["nlbyte"]
+            and np.array_equal(a["data"], b["data"]) for a, b in zip(want, got))
+        nblk += len(want)
+        if not same:
+            bad.append(int(chn))
+    return {"ok": not bad and nblk > 0, "channels": len(sel), "blocks": int(nblk), "mismatching_channels": bad,
+            "checker": "reference d8psk.c (oracle/_ref, -O2)" if kind == "ref" else "oracle port",
+            "what": "completed blocks (trigger/end position, nbrow, nlbyte, data[8][255]) bit exact"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -252,12 +296,15 @@ def run_ours(args, rank, local_rank, world):
     def step():
         g.process_device(x.data_ptr(), ns, x.stride(0))
 
-    # ---- warm-up (also validates: every placed burst must come back as a block)
-    blocks_seen = 0
-    for _ in range(args.warmup):
+    # ---- warm-up (also validates: every placed burst must come back as a block -- checked below on the FIRST step,
+    #      which starts from a fresh state; later steps re-feed the buffer with carried state, so their seams add events)
+    blocks_seen, blocks_first = 0, None
+    for _ in range(max(1, args.warmup)):
         step()
         g.sync()
         blocks_seen = len(g.drain_blocks())
+        if blocks_first is None:
+            blocks_first = blocks_seen
     # ---- timed region: K launches, CUDA events on the launching stream, barrier + sync both sides
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -297,6 +344,15 @@ def run_ours(args, rank, local_rank, world):
     ms_max = float(t.item())
     units = nch * ns * args.steps * world  # channel-samples over all ranks
     value = units / (ms_max * 1e-3) / 1e6
+
+    # ---- self-check of what was timed: channels of the timed tensor through a fresh handle vs the CPU oracle, blocks bit exact
+    parity = None
+    if rank == 0 and not args.no_check:
+        parity = self_check(x, chans, fos, ns, cps, local_rank, args.check_channels)
+        if not parity["ok"]:
+            raise SystemExit("bench.py: the timed workload does NOT decode like the oracle: " + json.dumps(parity))
+    if blocks_first < nbursts - max(2, nbursts // 200):   # a burst cut by the end of the buffer may be missing
+        raise SystemExit(f"bench.py: {nbursts} bursts placed per step but only {blocks_first} blocks came back from the first step")
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + drain inside the timed region)
     e2e = None
@@ -409,7 +465,7 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1),
                    "launch_mode": "back-to-back launches with programmatic dependent launch (tails overlap)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "link": link,
+        "parity_checked": parity, "blocks_first_step": blocks_first, "link": link,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

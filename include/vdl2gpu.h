@@ -56,6 +56,9 @@ enum vdl2_format {
    the integer dot-product mixer that is the default for 8-bit input at 2 Msps; same outputs within the
    parity tolerance, slower; for A/B tests */
 #define VDL2_OPT_FLOAT_MIX 0x200u
+/* option bit: mix cu8/cs8 input at 2 Msps with the IDP.4A integer mixer of round 1 instead of the int8 tensor-core
+   mixer that is the default since ABI version 4 (same exact integer sums, slower; for A/B tests) */
+#define VDL2_OPT_DP4A_MIX 0x800u
 /* option bit: let consecutive vdl2_process_device() launches overlap (programmatic dependent launch: the next launch's
    warps move in while the tail of the previous one drains; the per-channel order is kept by the kernel's own flags).
    No per-launch events are recorded then: vdl2_stats_t.last_kernel_ms stays 0 -- bracket with your own events on

@@ -39,8 +39,39 @@ def avlc(frames: np.ndarray) -> np.ndarray:
     return recs
 
 
+MMA_LIB = os.path.join(HERE, "libvdl2mmaemul.so")
+_mma = None
+
+
+def build_mma():
+    src = os.path.join(HERE, "mma_mix_host.cpp")
+    csrc = os.path.join(ROOT, "vdlm2dec_b200", "csrc")
+    deps = [src, os.path.join(csrc, "vdl2_mma_tables.h"), os.path.join(csrc, "vdl2_common.h")]
+    if os.path.exists(MMA_LIB) and all(os.path.getmtime(MMA_LIB) >= os.path.getmtime(d) for d in deps):
+        return MMA_LIB
+    cuda_inc = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-fPIC", "-shared", f"-I{cuda_inc}", f"-I{csrc}",
+                    "-o", MMA_LIB, src], check=True)
+    return MMA_LIB
+
+
+def mma_mix(rows: np.ndarray, Fo: int, cu8: bool = True, fs: int = 2_000_000, sdrclk: int = 500):
+    """Lane-level replay of the int8 tensor-core mixer (mix_rows_mma) on the product's host tables: rows = (<= 32, 2 * fs/1000)
+    8-bit IQ bytes -> (complex64 dumps [32 * 84] in time order, protocol error count)."""
+    global _mma
+    if _mma is None:
+        _mma = C.CDLL(build_mma())
+    rows = np.ascontiguousarray(rows)
+    assert rows.ndim == 2 and rows.shape[0] <= 32 and rows.shape[1] == 2 * (fs // 1000) and rows.dtype.itemsize == 1
+    out = np.zeros((32, 84, 2), np.float32)
+    rc = _mma.emul_mma_mix(rows.ctypes.data_as(C.c_void_p), rows.shape[0], C.c_uint(fs), C.c_uint(sdrclk), int(Fo), int(cu8),
+                           out.ctypes.data_as(C.c_void_p))
+    return (out[..., 0] + 1j * out[..., 1]).astype(np.complex64).reshape(-1), rc
+
+
 def build():
     build_avlc()
+    build_mma()
     src = os.path.join(HERE, "emul_main.cpp")
     deps = [src, os.path.join(HERE, "vdl2_emul.h")] + [os.path.join(ROOT, "vdlm2dec_b200", "csrc", f)
                                                         for f in ("vdl2_demod.cuh", "vdl2_common.h", "vdl2_tables.h")]

@@ -4,10 +4,35 @@ from __future__ import annotations
 
 import numpy as np
 
+from oracle import pyoracle
 from oracle.pyoracle import Oracle
 from vdlm2dec_b200 import synth
 
 D_TOL = 1e-5  # rad, absolute: the north_star's soft-symbol tolerance (DESIGN.md "numerics")
+
+
+def oracle_kind() -> str:
+    """The checker the parity tests compare against: the REFERENCE's own d8psk.c + viterbi.c compiled in place (oracle/_ref,
+    strict -O2; built here, travels to the GPU box) whenever it is present and loads, else the independent port.  The port is
+    pinned bit for bit against the reference in tests/test_oracle.py (CPU tier) and again on the GPU box
+    (tests/test_gpu_parity.py::test_port_equals_reference_on_this_box)."""
+    global _KIND
+    if _KIND is None:
+        _KIND = "port"
+        if pyoracle.available("ref"):
+            try:
+                pyoracle.load("ref")
+                _KIND = "ref"
+            except OSError:
+                pass
+    return _KIND
+
+
+_KIND = None
+
+
+def oracle(chn=0, Fr=136_975_000, Fo=-50_000, fs=2_000_000, sdrclk=500, kind=None, **kw) -> Oracle:
+    return Oracle(kind or oracle_kind(), chn=chn, Fr=Fr, Fo=Fo, fs=fs, sdrclk=sdrclk, **kw)
 
 
 def make_channels(nch, nsamples, seed=1, fs=2_000_000, fmt="cu8", period=60000, fos=None, **kw):
@@ -22,8 +47,8 @@ def make_channels(nch, nsamples, seed=1, fs=2_000_000, fmt="cu8", period=60000, 
     return specs, np.stack(iqs)
 
 
-def run_oracle(iq_row, Fo, fmt="cu8", kind="port", fs=2_000_000, sdrclk=500, chn=0, Fr=136_975_000):
-    o = Oracle(kind, chn=chn, Fr=Fr, Fo=Fo, fs=fs, sdrclk=sdrclk)
+def run_oracle(iq_row, Fo, fmt="cu8", kind=None, fs=2_000_000, sdrclk=500, chn=0, Fr=136_975_000):
+    o = Oracle(kind or oracle_kind(), chn=chn, Fr=Fr, Fo=Fo, fs=fs, sdrclk=sdrclk, real_input=(fmt == "f32real"))
     o.feed(iq_row, fmt)
     return o
 

@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 
 from oracle.pyoracle import Oracle
-from tests.parity_util import compare_channel, make_channels, run_oracle
+from tests.parity_util import compare_channel, make_channels, oracle, oracle_kind, run_oracle
 from vdlm2dec_b200 import synth
-from vdlm2dec_b200.api import OPT_EXACT_IDLE, OPT_FLOAT_MIX, OPT_OVERLAP, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
+from vdlm2dec_b200.api import OPT_DP4A_MIX, OPT_EXACT_IDLE, OPT_FLOAT_MIX, OPT_OVERLAP, TAP_DUMPS, TAP_STEPS, TAP_SYMS, TAP_SYNCS, Vdl2Gpu
 
 pytestmark = pytest.mark.gpu
 ALL_TAPS = TAP_DUMPS | TAP_STEPS | TAP_SYNCS | TAP_SYMS  # TAP_STEPS implies the exact fit at every idle step
@@ -46,24 +46,48 @@ def test_parity_formats(fmt, screen):
     assert g.stats()["kernel_launches"] == 1
 
 
+def test_port_equals_reference_on_this_box():
+    """Re-pin of the independent port against the reference's own d8psk.c + viterbi.c (oracle/_ref/libvdl2ref_O2.so, built from
+    the read-only mount and shipped with the snapshot) ON THE GPU BOX, with this box's libm: every tap T1..T6 bit identical."""
+    from oracle import pyoracle
+    if oracle_kind() != "ref":
+        pytest.skip("oracle/_ref not present on this box")
+    specs, iq = make_channels(3, 700_000, seed=77)
+    for c, spec in enumerate(specs):
+        a = Oracle("ref", chn=c, Fo=spec.Fo).feed(iq[c])
+        b = Oracle("port", chn=c, Fo=spec.Fo).feed(iq[c])
+        assert len(a.blocks) >= 1
+        for tap in ("dumps", "steps", "syncs", "syms", "blocks"):
+            assert getattr(a, tap).tobytes() == getattr(b, tap).tobytes(), f"port != reference at tap {tap} (channel {c})"
+
+
 @pytest.mark.parametrize("fmt", ["cu8", "cs8"])
-def test_parity_float_mixer_for_8bit_input(fmt):
-    """8-bit input defaults to the integer dot-product mixer (exact int32 sums, weights quantised to 2^-22);
-    OPT_FLOAT_MIX selects the generic fp32 mixer all other formats use.  Both must meet the same parity bars,
-    and must agree with each other on every block."""
+def test_parity_three_mixers_for_8bit_input(fmt):
+    """8-bit input at 2 Msps defaults to the int8 tensor-core mixer (mma.sync m16n8k32, exact int32 sums, weights quantised
+    to 2^-22); OPT_DP4A_MIX selects the IDP.4A mixer of round 1 (the same integer sums), OPT_FLOAT_MIX the generic fp32
+    mixer all other formats use.  All three must meet the same parity bars and agree with each other on every block;
+    the two integer mixers must agree on the decimated stream to the last bit but one (same sums, different fp32 combine order)."""
     nch, n = 4, 900_000
     specs, iq = make_channels(nch, n, seed=5, fmt=fmt)
     chans = [(c, 136_975_000, specs[c].Fo) for c in range(nch)]
-    a = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS | OPT_FLOAT_MIX, max_samples=n)
-    a.process(iq)
-    ba = a.drain_blocks()
-    reps = _check_all(a, specs, iq, fmt, blocks=ba, steps=False)
-    assert sum(r["blocks"][0] for r in reps) >= nch
-    b = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS, max_samples=n)
-    b.process(iq)
-    bb = b.drain_blocks()
-    assert len(ba) == len(bb) and np.array_equal(ba["data"], bb["data"]) and np.array_equal(ba["sync_dump"], bb["sync_dump"])
-    _check_all(b, specs, iq, fmt, blocks=bb, steps=False)
+    res = {}
+    for name, opt in (("float", OPT_FLOAT_MIX), ("dp4a", OPT_DP4A_MIX), ("mma", 0)):
+        g = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS | opt, max_samples=n)
+        g.process(iq)
+        blocks = g.drain_blocks()
+        res[name] = (blocks, [g.read_dumps(c) for c in range(nch)])   # reading clears the tap: _check_all gets its own handle
+        h = Vdl2Gpu(chans, fmt=fmt, taps=SCREEN_TAPS | opt, max_samples=n)
+        h.process(iq)
+        reps = _check_all(h, specs, iq, fmt, steps=False)
+        assert sum(r["blocks"][0] for r in reps) >= nch
+    ba = res["float"][0]
+    for name in ("dp4a", "mma"):
+        bb = res[name][0]
+        assert len(ba) == len(bb) and np.array_equal(ba["data"], bb["data"]) and np.array_equal(ba["sync_dump"], bb["sync_dump"])
+    for c in range(nch):
+        a, b = res["dp4a"][1][c], res["mma"][1][c]
+        rms = np.sqrt(np.mean(np.abs(a) ** 2))
+        assert len(a) == len(b) and np.abs(a - b).max() < 1e-6 * rms
 
 
 @pytest.mark.parametrize("fmt,fs,sdrclk,fos", [
@@ -84,7 +108,7 @@ def test_parity_other_rates_and_formats(fmt, fs, sdrclk, fos):
     blocks = g.drain_blocks()
     total = 0
     for c, spec in enumerate(specs):
-        o = Oracle("port", chn=c, Fo=spec.Fo, fs=fs, sdrclk=sdrclk).feed(iq[c], fmt)
+        o = oracle(chn=c, Fo=spec.Fo, fs=fs, sdrclk=sdrclk, real_input=(fmt == "f32real")).feed(iq[c], fmt)
         gd = g.read_dumps(c)
         assert len(gd) == n // (fs // 1000) * 84
         rep = compare_channel(o, blocks[blocks["chn"] == c], g.read_syncs(c), g.read_syms(c), gd, None, ndump_limit=len(gd))
@@ -106,7 +130,7 @@ def test_two_handles_with_different_rates_interleaved():
     _check_all(a, sa, ia, "cu8", steps=False)
     blocks = b.drain_blocks()
     for c, spec in enumerate(sb):
-        o = Oracle("port", chn=c, Fo=spec.Fo, fs=6_000_000, sdrclk=1500).feed(ib[c], "f32real")
+        o = oracle(chn=c, Fo=spec.Fo, fs=6_000_000, sdrclk=1500, real_input=True).feed(ib[c], "f32real")
         gd = b.read_dumps(c)
         compare_channel(o, blocks[blocks["chn"] == c], b.read_syncs(c), b.read_syms(c), gd, None, ndump_limit=len(gd))
 
@@ -148,7 +172,7 @@ def test_parity_shared_stream_8_channels():
     blocks = g.drain_blocks()
     total = 0
     for c, fo in enumerate(fos):
-        o = Oracle("port", chn=c, Fr=136_000_000 + fo, Fo=fo).feed(iq)
+        o = oracle(chn=c, Fr=136_000_000 + fo, Fo=fo).feed(iq)
         gd = g.read_dumps(c)
         rep = compare_channel(o, blocks[blocks["chn"] == c], g.read_syncs(c), g.read_syms(c), gd, g.read_steps(c), ndump_limit=len(gd))
         total += rep["blocks"][0]

@@ -141,3 +141,29 @@ def test_phase2_noise_free_tail_is_the_only_place_phase_is_ill_conditioned():
     assert (loud[off] < 0.01 * burst_level).all() and (dev[loud > 0.05 * burst_level] < 1e-5).all()
     assert np.array_equal(sm["gi"], osm["gi"]) and np.array_equal(sm["v"] > 0.5, osm["v"] > 0.5)
     assert len(b) == len(o.blocks) and all(np.array_equal(x["data"], y["data"]) for x, y in zip(b, o.blocks))
+
+
+@pytest.mark.parametrize("fmt", ["cu8", "cs8"])
+def test_tensor_core_mixer_tables_and_lane_math_match_oracle(fmt):
+    """The int8 tensor-core mixer (mix_rows_mma, vdl2_kernel.cu) replayed lane by lane on the CPU from the product's own host
+    tables (vdl2_mma_tables.h): TMA box ring with its wait/release schedule, ldmatrix addressing under the 64B swizzle,
+    m16n8k32 fragments, dump masks, accumulator start values, FFMA2/shuffle epilogue.  Its decimated stream must match the
+    oracle's T1 tap (d8psk.c:366-381) like the kernel's has to, for full and ragged tiles, with zero protocol errors."""
+    from oracle.pyoracle import TAP_DUMPS, Oracle
+    from tests import emul
+    from vdlm2dec_b200 import synth
+    worst = 0.0
+    for k, (Fo, nrows) in enumerate([(-50_000, 32), (125_000, 32), (-450_000, 7), (425_000, 32), (300_000, 1)]):
+        n = nrows * 2000
+        spec = synth.standard_channel(seed=900 + k, nsamples=n, Fo=Fo, period=20_000)
+        iq = synth.render_channel(spec, n, fmt=fmt)
+        got, rc = emul.mma_mix(iq.view(np.uint8).reshape(nrows, 4000), Fo, cu8=(fmt == "cu8"))
+        assert rc == 0, f"{rc} ring protocol errors"
+        want = Oracle("port", Fo=Fo, taps=TAP_DUMPS).feed(iq, fmt).dumps
+        assert len(want) == nrows * 84
+        rms = np.sqrt(np.mean(np.abs(want) ** 2))
+        err = np.abs(got[:len(want)] - want).max() / rms
+        worst = max(worst, err)
+        assert err < 1e-6, f"Fo {Fo} rows {nrows}: decimated stream deviates {err:.2e} of rms"
+        assert np.isfinite(got.view(np.float32)).all()   # rows past the end of a short tile (zero-filled boxes) are never read, but stay finite
+    assert worst > 0.0

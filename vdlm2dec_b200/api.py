@@ -25,6 +25,7 @@ FMT_BYTES = {"cu8": 2, "cs8": 2, "cs16": 4, "cf32": 8, "f32real": 4}
 TAP_DUMPS, TAP_STEPS, TAP_SYNCS, TAP_SYMS = 1, 2, 4, 8
 OPT_EXACT_IDLE = 0x100
 OPT_OVERLAP = 0x400  # consecutive launches may overlap (PDL); no per-launch kernel time
+OPT_DP4A_MIX = 0x800  # cu8/cs8 at 2 Msps: round-1 IDP.4A mixer instead of the int8 tensor-core mixer (A/B, parity tests)
 OPT_FLOAT_MIX = 0x200  # cu8/cs8: generic fp32 mixer instead of the integer dot-product mixer (A/B, parity tests)
 
 STEP_DT = np.dtype([("dump", "<i8"), ("P", "<f4"), ("err", "<f4"), ("fr", "<f4"), ("pad", "<i4")])

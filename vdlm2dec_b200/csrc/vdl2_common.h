@@ -19,6 +19,11 @@
 #define VDL2_SCHED_SLOTS 16	/* distinct (fs, SDRCLK, format) combinations alive in one process */
 #define VDL2_W8_PHASES 104	/* integer mixer: oscillator entries by NCO phase, 80 + 24 so that a dump never wraps */
 #define VDL2_W8_ENTRIES 120	/* ... plus 16 "first sample only" entries closing the 23-sample dumps of a row */
+#define VDL2_MM_PHASES 10	/* int8 tensor-core mixer: window phases = NCO period / 8 samples (80 / 8 at 2 Msps) */
+#define VDL2_MM_BT_ENTRIES (VDL2_MM_PHASES * 24)	/* uint4 per (phase, column 0..5, lane & 3): B fragments */
+#define VDL2_MM_DT_ENTRIES ((VDL2_DUMPS_PER_ROW + 1) * 4)	/* int4 per (dump, lane & 3): accumulator start, scale, offset correction; +1: prefetch */
+#define VDL2_MM_W 0x1u		/* schedule word bits of the tensor-core mixer, see vdl2_mma_tables.h */
+#define VDL2_MM_R 0x2u
 #define VDL2_SCR_WORDS 512	/* descrambler sequence: 25 + 8*8*255 = 16345 bits max */
 
 #define VDL2_FLAG_NO_SCREEN 1u	/* debug: run the exact 17-point fit at every idle step */

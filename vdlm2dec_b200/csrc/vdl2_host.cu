@@ -26,6 +26,7 @@
 #include "vdl2_kernel.h"
 #include "vdl2_link.h"
 #include "vdl2_tables.h"
+#include "vdl2_mma_tables.h"
 
 static_assert(sizeof(Vdl2BlockRec) == sizeof(vdl2_block_t), "block record layout");
 static_assert(sizeof(Vdl2StepRec) == sizeof(vdl2_step_t), "step record layout");
@@ -52,7 +53,8 @@ struct vdl2gpu {
 	float4 *d_dcorr;
 	uint4 *d_w8;		/* integer mixer tables (dp4a mode only) */
 	float *d_soft;		/* soft-demap tables for per-lane look-ups */
-	int dp4a;		/* 1: cu8/cs8 at a rate whose dumps are 23/24 samples -> integer dot-product mixer */
+	int dp4a;		/* mixer of cu8/cs8 input at a rate whose dumps are 23/24 samples (2 Msps): 2 = int8 tensor cores (default),
+				   1 = IDP.4A (VDL2_OPT_DP4A_MIX); 0 = the generic fp32 mixer (every other format / rate) */
 	int sched_slot;
 	unsigned *d_ticket;
 	unsigned *d_slotmask;
@@ -157,6 +159,10 @@ static void build_tables(Vdl2Tables & t, unsigned *sched_dump, const vdl2gpu * h
 	/* dump schedule of one row (d8psk.c:374-381): dump k ends after sample e_k; it consists of np whole
 	   chunks plus the chunk holding e_k (np counts from the chunk after the previous boundary chunk) */
 	int clk = 0, k = 0, prev_c = -1;
+	if (h->dp4a == 2) {
+		vdl2_mma_build_sched(h->row_samples, (int)h->cfg.sdrclk, h->cfg.fs / VDL2_STEPRATE, VDL2_DUMPS_PER_ROW, sched_dump);
+		return;
+	}
 	if (h->dp4a) {
 		/* integer mixer: per dump (first sample << 16) | (table entry of its 12th sample pair << 8) | entry of its
 		   first pair.  Entries 0..103 are indexed by NCO phase; a 23-sample dump closes with one of the
@@ -192,6 +198,8 @@ static void build_tables(Vdl2Tables & t, unsigned *sched_dump, const vdl2gpu * h
 	}
 }
 
+static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, const cudaDeviceProp & prop);
+
 extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, vdl2gpu_t ** out)
 {
 	if (!cfg || !chans || !out)
@@ -216,7 +224,23 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		return fail(NULL, "vdl2_create: device %d is sm_%d%d; the kernels are built for sm_100a only", cfg->device, prop.major,
 			    prop.minor);
 
-	vdl2gpu *h = new vdl2gpu();
+	/* everything after this point can fail half way (out of memory, driver entry points ...): the partially built handle is
+	   torn down by the same code as a complete one, and its message moves to the create-error slot the caller can read
+	   through vdl2_last_error(NULL) */
+	vdl2gpu *h = new vdl2gpu();	/* value-initialised: every pointer null, every flag false */
+	const int rc = create_body(h, cfg, chans, prop);
+	if (rc) {
+		g_create_error = h->err;
+		vdl2_destroy(h);
+		return rc;
+	}
+	*out = h;
+	return 0;
+}
+
+static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, const cudaDeviceProp & prop)
+{
+	cudaError_t e = cudaSuccess;
 	h->cfg = *cfg;
 	h->nstreams = cfg->nch / cfg->ch_per_stream;
 	h->bytes_per_sample = fmt_bytes(cfg->format);
@@ -239,11 +263,10 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->rows_done = 0;
 	memset(&h->st, 0, sizeof h->st);
 	if (h->row_bytes % 16 || h->row_bytes / 16 > VDL2_MAX_CHUNKS) {
-		delete h;
-		return fail(NULL, "vdl2_create: row of %d bytes is not a whole number of 16-byte chunks", h->row_bytes);
+		return fail(h, "vdl2_create: row of %d bytes is not a whole number of 16-byte chunks", h->row_bytes);
 	}
 	h->chunks_per_row = h->row_bytes / 16;
-	h->nbox = (h->row_bytes + 127) / 128;
+	h->nbox = (h->row_bytes + 127) / 128;	/* generic mixer: 128-byte column boxes; the tensor-core mixer sets its own below */
 	const int nco_n = cfg->fs / VDL2_STEPRATE;	/* d8psk.c:348 */
 	h->nco_entries = (cfg->format == VDL2_FMT_CF32) ? nco_n : nco_n / 2;
 	h->n_sm = prop.multiProcessorCount;
@@ -265,6 +288,10 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 			}
 		}
 		h->dp4a = ok && nshort <= VDL2_W8_ENTRIES - VDL2_W8_PHASES;
+		/* the tensor-core mixer unless the caller asks for the IDP.4A one (A/B) */
+		if (h->dp4a && !(cfg->taps & VDL2_OPT_DP4A_MIX) && !getenv("VDL2_DP4A_MIX")
+		    && vdl2_mma_usable(h->row_samples, (int)cfg->sdrclk, nco_n, VDL2_DUMPS_PER_ROW, VDL2_MM_PHASES))
+			h->dp4a = 2;
 	}
 
 	/* dump schedule sanity: exactly 84 dumps per row, clock back at 0, <= 1 boundary per chunk */
@@ -276,15 +303,13 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 				clk %= (int)cfg->sdrclk;
 				k++;
 				if (n / h->spc == lastc) {
-					delete h;
-					return fail(NULL, "vdl2_create: two dump boundaries in one chunk (fs too low)");
+					return fail(h, "vdl2_create: two dump boundaries in one chunk (fs too low)");
 				}
 				lastc = n / h->spc;
 			}
 		}
 		if (k != VDL2_DUMPS_PER_ROW || clk != 0) {
-			delete h;
-			return fail(NULL, "vdl2_create: fs=%u sdrclk=%u gives %d dumps/ms (clk %d), need 84 (0)", cfg->fs, cfg->sdrclk, k, clk);
+			return fail(h, "vdl2_create: fs=%u sdrclk=%u gives %d dumps/ms (clk %d), need 84 (0)", cfg->fs, cfg->sdrclk, k, clk);
 		}
 	}
 
@@ -314,8 +339,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 				h->sched_slot = i;
 		if (h->sched_slot < 0) {
 			if (nslots == VDL2_SCHED_SLOTS) {
-				delete h;
-				return fail(NULL, "vdl2_create: more than %d distinct (fs, sdrclk, format) combinations in one process", VDL2_SCHED_SLOTS);
+				return fail(h, "vdl2_create: more than %d distinct (fs, sdrclk, format) combinations in one process", VDL2_SCHED_SLOTS);
 			}
 			slots[nslots].fs = cfg->fs;
 			slots[nslots].sdrclk = cfg->sdrclk;
@@ -327,8 +351,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		e = (cudaError_t) vdl2_kernel_upload_sched(h->sched_slot, sched_dump);
 	}
 	if (e != cudaSuccess) {
-		delete h;
-		return fail(NULL, "vdl2_create: constant table upload failed: %s", cudaGetErrorString(e));
+		return fail(h, "vdl2_create: constant table upload failed: %s", cudaGetErrorString(e));
 	}
 
 	/* longest dump in chunks (+1 boundary chunk) times entries per chunk: how far past the table a dump can read */
@@ -336,8 +359,7 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	h->smem = vdl2_kernel_smem_bytes(h->nco_entries + h->wext, h->dp4a);
 	e = (cudaError_t) vdl2_kernel_occupancy(cfg->format, h->dp4a, h->smem, &h->ctas_per_sm);
 	if (e != cudaSuccess || h->ctas_per_sm < 1) {
-		delete h;
-		return fail(NULL, "vdl2_create: kernel does not fit (smem %d B): %s", h->smem, cudaGetErrorString(e));
+		return fail(h, "vdl2_create: kernel does not fit (smem %d B): %s", h->smem, cudaGetErrorString(e));
 	}
 	h->grid = h->n_sm * h->ctas_per_sm;
 	h->st.n_sm = h->n_sm;
@@ -419,7 +441,27 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
 	}
 
-	if (h->dp4a) {
+	if (h->dp4a == 2) {
+		/* tensor-core mixer: B fragments per window phase and per-dump accumulator start / scale / correction
+		   (vdl2_mma_tables.h); they travel in the w8 / dcorr slots of the kernel parameters */
+		static_assert(sizeof(Vdl2MmaU4) == sizeof(uint4) && sizeof(Vdl2MmaI4) == sizeof(float4), "table entry layout");
+		std::vector < Vdl2MmaU4 > bt((size_t) nch * VDL2_MM_BT_ENTRIES);
+		std::vector < Vdl2MmaI4 > dt((size_t) nch * VDL2_MM_DT_ENTRIES);
+		std::vector < float >wr(nco_n), wi(nco_n);
+		for (int c = 0; c < nch; c++) {
+			vdl2_nco_table(chans[c].Fo, cfg->fs, nco_n, wr.data(), wi.data());
+			vdl2_mma_build_chan(wr.data(), wi.data(), nco_n, h->row_samples, (int)cfg->sdrclk, VDL2_DUMPS_PER_ROW, cfg->format == VDL2_FMT_CU8,
+					    bt.data() + (size_t) c * VDL2_MM_BT_ENTRIES, dt.data() + (size_t) c * VDL2_MM_DT_ENTRIES);
+		}
+		unsigned sched_tmp[VDL2_DUMPS_PER_ROW];
+		h->nbox = vdl2_mma_build_sched(h->row_samples, (int)cfg->sdrclk, nco_n, VDL2_DUMPS_PER_ROW, sched_tmp);
+		CK(h, cudaMalloc(&h->d_w8, sizeof(uint4) * bt.size()));
+		CK(h, cudaMemcpy(h->d_w8, bt.data(), sizeof(uint4) * bt.size(), cudaMemcpyHostToDevice));
+		CK(h, cudaFree(h->d_dcorr));
+		h->d_dcorr = NULL;
+		CK(h, cudaMalloc(&h->d_dcorr, sizeof(float4) * dt.size()));
+		CK(h, cudaMemcpy(h->d_dcorr, dt.data(), sizeof(float4) * dt.size(), cudaMemcpyHostToDevice));
+	} else if (h->dp4a) {
 		/* integer mixer tables.  W = round(w * 2^22) of the reference's float oscillator value, split into balanced
 		   base-256 digits W = d2*65536 + d1*256 + d0 (each in [-128,127], |d2| <= 64).  The kernel accumulates
 		     re_acc = sum Is*wr + (~Qs)*wi = sum Is*wr - Qs*wi - sum wi,    im_acc = sum Qs*wr + Is*wi
@@ -550,7 +592,6 @@ extern "C" int vdl2_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * 
 	CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_fn, cudaEnableDefault, &qres));
 	if (!h->encode_fn || qres != cudaDriverEntryPointSuccess)
 		return fail(h, "vdl2_create: cuTensorMapEncodeTiled not available from the driver");
-	*out = h;
 	return 0;
 }
 
@@ -559,7 +600,8 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	if (!h)
 		return 0;
 	cudaSetDevice(h->cfg.device);
-	cudaStreamSynchronize(h->stream);
+	if (h->stream)
+		cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
@@ -587,9 +629,12 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 		cudaEventDestroy(h->lev0);
 		cudaEventDestroy(h->lev1);
 	}
-	cudaEventDestroy(h->ev0);
-	cudaEventDestroy(h->ev1);
-	cudaStreamDestroy(h->stream);
+	if (h->ev0)
+		cudaEventDestroy(h->ev0);
+	if (h->ev1)
+		cudaEventDestroy(h->ev1);
+	if (h->stream)
+		cudaStreamDestroy(h->stream);
 	delete h;
 	return 0;
 }

@@ -468,8 +468,182 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
 	}
 }
 
+/* ------------------------------------------------------------------ phase 1, 8-bit formats at 2 Msps: int8 tensor-core mixer
+ *
+ * With one row per lane the mixer is a dense integer contraction (vdl2_mma_tables.h has the algebra): per dump
+ *     C[32 rows x 8] = A[32 rows x 64 window bytes] * B[64 x 8]      4 x mma.sync.m16n8k32 (u8 or s8 data, s8 weights, int32 sums)
+ * instead of 72 IDP.4A + 24 PRMT + 24 LOP3 per row: the raw I,Q bytes ARE the A operand (no conversion, not even a sign flip:
+ * unsigned bytes are undone exactly by the accumulator's start value), re and im get their own weight columns (digits 2,1,0 of
+ * the 2^-22-quantised oscillator value), and the accumulator starts at the bits of 1.5 * 2^23 so that it leaves the tensor
+ * core as a float.  Same exact int32 sums as the IDP.4A mixer, so parity is untouched.
+ *   - HBM -> shared memory: NON-overlapping TMA boxes of 32 rows x 64 bytes (64B swizzle) in a ring; a dump's window is the four
+ *     16-byte chunks j0..j0+3 wherever they lie in the ring (at most two boxes), addressed chunk by chunk through ldmatrix.x4
+ *     (conflict free under the swizzle).  Every input byte crosses L2 -> SM exactly once (the per-dump windows of the IDP.4A
+ *     mixer overlapped: 1.14x DRAM traffic).
+ *   - B: per channel one table of 10 window phases (the NCO period is 80 samples = 10 chunks) x 6 columns in fragment order,
+ *     one LDS.128 per lane and dump; the samples of the window that belong to the neighbouring dumps are masked with three
+ *     shifts (first/last sample of the dump from the schedule word).
+ *   - epilogue: lane (g, t) holds columns 2t, 2t+1 of rows g, g+8 (+16 for the second m16 tile).  t even: digits 2 and 1,
+ *     t odd: digit 0 (and a duplicate column times zero); one shuffle with lane^1 completes the value, even lanes keep the
+ *     first m16 tile and odd lanes the second; t < 2 is the real part, t >= 2 the imaginary part.
+ */
+#define MM_NST VDL2_MM_NST
+#define MM_STAGE 2048		/* 32 rows x 64 bytes */
+#define MM_TPITCH 9		/* floats per row of one plane of the transpose tile */
+#define MM_TPLANE 296		/* floats between the real and the imaginary plane: 32 * 9 + 8 keeps the four lane groups on distinct banks */
+#define MM_TILE_BYTES (2 * MM_TPLANE * 4)
+
+template < int FMT > __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t(&a)[4], uint32_t b0, uint32_t b1)
+{
+	if (FMT == VDL2_FMT_CU8)
+		asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};":"+r" (c[0]),
+			      "+r"(c[1]), "+r"(c[2]), "+r"(c[3]):"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+	else
+		asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};":"+r" (c[0]),
+			      "+r"(c[1]), "+r"(c[2]), "+r"(c[3]):"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t(&a)[4], uint32_t addr)
+{
+	asm volatile ("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];":"=r" (a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]):"r"(addr));
+}
+
+/* shifts with PTX semantics: amounts >= 32 give 0 (the C operators are undefined there) */
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
+{
+	uint32_t r;
+	asm("shl.b32 %0, %1, %2;":"=r"(r):"r"(v), "r"(n));
+	return r;
+}
+
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n)
+{
+	uint32_t r;
+	asm("shr.u32 %0, %1, %2;":"=r"(r):"r"(v), "r"(n));
+	return r;
+}
+
+/* one elected lane (the warp is converged): lets ptxas issue the TMA from uniform registers without a broadcast loop */
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t p;
+	asm volatile ("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}":"=r" (p));
+	return p != 0;
+}
+
+/* loop invariants the compiler would otherwise recompute inside the dump loop (it rematerialises cheap per-lane values at
+   128 registers): an empty asm makes the value opaque, so it stays in its register */
+#define VDL2_PIN(v) asm volatile ("" : "+r"(v))
+#define VDL2_PINF(v) asm volatile ("" : "+f"(v))
+
+template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensorMap * tmap, const Vdl2KParams & kp, unsigned char *stage0,
+								unsigned long long *bars, float *tile, const uint4 * bt, uint32_t & phases, int row0,
+								int stream, const int4 * dtab, float2 * sd, unsigned long long l2pol)
+{
+	const int lane = threadIdx.x;
+	const unsigned *sched = c_tab.sched_slots[kp.sched_slot];
+	const int g = lane >> 2, t = lane & 3;
+	/* ldmatrix.x4: lane l supplies row l & 7 of matrix l >> 3; matrix i = rows 8 (i & 1) .. +7 of an m16 tile, window chunk
+	   2 s + (i >> 1).  64B-swizzled box: chunk c of row r sits at r * 64 + ((c ^ ((r >> 1) & 3)) << 4).  Chunk numbers are
+	   kept multiplied by 16 (byte offsets). */
+	uint32_t sw16 = ((uint32_t) (lane >> 1) & 3u) << 4, cwl16 = ((uint32_t) lane >> 4) << 4;
+	uint32_t rowoff = smem_u32(stage0) + (((uint32_t) lane >> 3) & 1u) * 512u + ((uint32_t) lane & 7u) * 64u;
+	uint32_t btl = smem_u32(bt + ((g >> 2) * 3 + min(g & 3, 2)) * 4 + t);	/* columns 3 and 7 re-read 2 and 5: finite, multiplied by 0 */
+	const int4 *dp = dtab + t;
+	float scx = (t & 1) ? 1.f : 65536.f, scy = (t & 1) ? 0.f : 256.f;
+	float nscx = -12582912.f * scx, nscy = -12582912.f * scy;	/* exact: powers of two */
+	int t32 = 32 * t;
+	uint32_t tw = smem_u32(tile + (t >> 1) * MM_TPLANE + (g + 16 * (t & 1)) * MM_TPITCH);	/* this lane's two rows: tw, tw + 8 rows */
+	uint32_t odd = (uint32_t) t & 1u;
+	VDL2_PIN(sw16);
+	VDL2_PIN(cwl16);
+	VDL2_PIN(rowoff);
+	VDL2_PIN(btl);
+	VDL2_PINF(scx);
+	VDL2_PINF(scy);
+	VDL2_PINF(nscx);
+	VDL2_PINF(nscy);
+	VDL2_PIN(t32);
+	VDL2_PIN(tw);
+	VDL2_PIN(odd);
+	const float2 sc = make_float2(scx, scy), nsc = make_float2(nscx, nscy);
+	const int nbox = kp.nbox;
+	int st = 0, box = 0;
+	int4 dn = __ldg(dp);
+	mbar_wait(smem_u32(bars), phases & 1u);
+	phases ^= 1u;
+#pragma unroll 1
+	for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
+		const int4 dc = dn;
+		const unsigned sk = sched[dk];
+		dp += 4;
+		dn = __ldg(dp);	/* the table carries one entry more than there are dumps */
+		const int st1 = (st + 1 == MM_NST) ? 0 : st + 1;
+		if (sk & VDL2_MM_W) {
+			mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
+			phases ^= 1u << st1;
+		}
+		const uint32_t base0 = rowoff + (uint32_t) st * MM_STAGE, base1 = rowoff + (uint32_t) st1 * MM_STAGE;
+		const uint32_t q0 = (sk & 0x30u) + cwl16, q1 = q0 + 32u;	/* 16 * (chunk of this lane's matrix counted from the box start) */
+		const uint32_t ad0 = (q0 >= 64u ? base1 : base0) + ((q0 ^ sw16) & 0x30u);
+		const uint32_t ad1 = (q1 >= 64u ? base1 : base0) + ((q1 ^ sw16) & 0x30u);
+		uint32_t a00[4], a01[4], a10[4], a11[4];	/* [m16 tile][k step] */
+		ldsm_x4(a00, ad0);
+		ldsm_x4(a10, ad0 + 1024u);
+		ldsm_x4(a01, ad1);
+		ldsm_x4(a11, ad1 + 1024u);
+		uint4 B;
+		asm volatile ("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];":"=r" (B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w):"r"(btl + ((sk & 0x3f00u) >> 2)));
+		const int o16 = (int)((sk >> 16) & 127u), te = t32 - (int)(sk >> 23);
+		B.x &= shl_clamp(0xffffffffu, (uint32_t) max(o16 - t32, 0));	/* samples 2t, 2t+1: keep those >= o */
+		B.z &= shr_clamp(0xffffffffu, (uint32_t) max(te + 288, 0));	/* samples 16+2t, 17+2t: keep those < e */
+		B.w &= shr_clamp(0xffffffffu, (uint32_t) max(te + 416, 0));	/* samples 24+2t, 25+2t */
+		int c0[4] = { dc.x, dc.y, dc.x, dc.y }, c1[4] = { dc.x, dc.y, dc.x, dc.y };
+		imma_16832 < FMT > (c0, a00, B.x, B.y);
+		imma_16832 < FMT > (c1, a10, B.x, B.y);
+		imma_16832 < FMT > (c0, a01, B.z, B.w);
+		imma_16832 < FMT > (c1, a11, B.z, B.w);
+		/* the accumulators are floats 12582912 + sum: remove the bias and weigh the digits in one exact FFMA2 each */
+		const float2 y0 = ffma2(make_float2(__int_as_float(c0[0]), __int_as_float(c0[1])), sc, nsc);
+		const float2 y1 = ffma2(make_float2(__int_as_float(c0[2]), __int_as_float(c0[3])), sc, nsc);
+		const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
+		const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
+		const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;	/* rows g, g + 8, g + 16, g + 24 */
+		const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
+		const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
+		const float sf = __int_as_float(dc.z), corr = __int_as_float(dc.w);
+		const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
+		const uint32_t twk = tw + 4u * ((uint32_t) dk & 7u);
+		asm volatile ("st.shared.f32 [%0], %1;"::"r" (twk), "f"(v0):"memory");
+		asm volatile ("st.shared.f32 [%0], %1;"::"r" (twk + 8 * MM_TPITCH * 4), "f"(v1):"memory");
+		__syncwarp();	/* every lane has consumed the window; the tile is complete for this dump */
+		if (sk & VDL2_MM_R) {
+			if (box + MM_NST < nbox && elect_one()) {
+				const uint32_t bar = smem_u32(bars + st);
+				mbar_expect_tx(bar, MM_STAGE);
+				tma_load_3d(smem_u32(stage0 + st * MM_STAGE), tmap, bar, (box + MM_NST) * 32, row0, stream, l2pol);
+			}
+			box++;
+			st = st1;
+		}
+		if ((dk & 7) == 7 || dk == VDL2_DUMPS_PER_ROW - 1) {
+			/* 8 (last group: 4) dumps x 32 rows -> scratch, 64 contiguous bytes per row */
+			const int k0 = dk & ~7, ng = dk - k0 + 1;
+			const int col = lane & 7, rsub = lane >> 3;
+			float2 *dst = sd + VDL2_HIST + k0 + col;
+#pragma unroll
+			for (int it = 0; it < 8; it++) {
+				const int r = it * 4 + rsub;
+				if (col < ng)
+					__stcg(dst + r * VDL2_DUMPS_PER_ROW, make_float2(tile[r * MM_TPITCH + col], tile[MM_TPLANE + r * MM_TPITCH + col]));
+			}
+			__syncwarp();
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ the kernel */
-template < int FMT, bool DP, bool TAPS > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
+template < int FMT, int DP, bool TAPS > __global__ void __launch_bounds__(32, VDL2_MIN_CTAS)
 #ifdef VDL2_KP_BYVALUE
 vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2KParams kp)
 #else
@@ -482,8 +656,9 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	const int lane = threadIdx.x;
 	unsigned char *stage0 = smem;
 	/* stages (+ the transpose tile of the integer mixer) | mbarriers | header soft bits | oscillator table */
-	constexpr int STAGES_BYTES = DP ? D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 : NSTAGE * STAGE_BYTES;
-	constexpr int NBAR = DP ? D8_NST : NSTAGE;
+	/* DP: 0 generic fp32 mixer, 1 IDP.4A mixer, 2 int8 tensor-core mixer */
+	constexpr int STAGES_BYTES = DP == 2 ? MM_NST * MM_STAGE + MM_TILE_BYTES : (DP ? D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 : NSTAGE * STAGE_BYTES);
+	constexpr int NBAR = DP == 2 ? MM_NST : (DP ? D8_NST : NSTAGE);
 	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + STAGES_BYTES);
 	float *hv = reinterpret_cast < float *>(smem + STAGES_BYTES + 64);
 	float4 *wsm = reinterpret_cast < float4 * >(hv + 32);
@@ -571,7 +746,22 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		const int nd = nrows * VDL2_DUMPS_PER_ROW;
 
 		const float4 *dcorr = kp.dcorr + (size_t) ch * VDL2_DUMPS_PER_ROW;
-		if (DP) {
+		if (DP == 2) {
+			/* ---- phase 1, int8 tensor-core mixer: non-overlapping 64-byte boxes, see mix_rows_mma ---- */
+			if (lane == 0) {
+				for (int b = 0; b < MM_NST; b++) {
+					const uint32_t bar = smem_u32(bars + b);
+					mbar_expect_tx(bar, MM_STAGE);
+					tma_load_3d(smem_u32(stage0 + b * MM_STAGE), &tmap, bar, b * 32, row0, stream, l2pol);
+				}
+			}
+			uint4 *btsm = reinterpret_cast < uint4 * >(wsm);
+			for (int i = lane; i < VDL2_MM_BT_ENTRIES; i += 32)
+				btsm[i] = __ldg(kp.w8 + (size_t) ch * VDL2_MM_BT_ENTRIES + i);
+			__syncwarp();
+			mix_rows_mma < FMT > (&tmap, kp, stage0, bars, reinterpret_cast < float *>(smem + MM_NST * MM_STAGE), btsm, phases, row0, stream,
+					      reinterpret_cast < const int4 * >(kp.dcorr) + (size_t) ch * VDL2_MM_DT_ENTRIES, sd, l2pol);
+		} else if (DP) {
 			/* ---- phase 1, integer mixer: dump-aligned boxes, see mix_rows_dp4a ---- */
 			if (lane == 0) {
 				for (int b = 0; b < D8_NST; b++) {
@@ -818,12 +1008,14 @@ __global__ void vdl2_nsmid_kernel(unsigned *out)
 /* ------------------------------------------------------------------ launch shims used by vdl2_host.cu */
 extern "C" int vdl2_kernel_smem_bytes(int nco_entries, int dp4a)
 {
+	if (dp4a == 2)
+		return MM_NST * MM_STAGE + MM_TILE_BYTES + 64 + 32 * 4 + VDL2_MM_BT_ENTRIES * 16;
 	if (dp4a)
 		return D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 + 64 + 32 * 4 + VDL2_W8_ENTRIES * 16;
 	return VDL2_NSTAGE * STAGE_BYTES + 64 + 32 * 4 + nco_entries * 16;
 }
 
-template < int FMT, bool DP, bool TAPS > static cudaError_t launch_fmt2(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem,
+template < int FMT, int DP, bool TAPS > static cudaError_t launch_fmt2(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem,
 									 cudaStream_t st)
 {
 	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -843,7 +1035,7 @@ template < int FMT, bool DP, bool TAPS > static cudaError_t launch_fmt2(const CU
 	return cudaLaunchKernelEx(&cfg, vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, tmap, kp);
 }
 
-template < int FMT, bool DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+template < int FMT, int DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
 {
 #ifdef VDL2_ALWAYS_TAPS
 	if (true)
@@ -858,24 +1050,31 @@ extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl
 {
 	const CUtensorMap & m = *reinterpret_cast < const CUtensorMap * >(tmap);
 	cudaStream_t st = (cudaStream_t) stream;
+	if (dp4a == 2) {
+		switch (fmt) {
+		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 2 > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 2 > (m, *kp, grid, smem, st);
+		}
+		return (int)cudaErrorInvalidValue;
+	}
 	if (dp4a) {
 		switch (fmt) {
-		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, true > (m, *kp, grid, smem, st);
-		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, true > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 1 > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 1 > (m, *kp, grid, smem, st);
 		}
 		return (int)cudaErrorInvalidValue;
 	}
 	switch (fmt) {
-	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, false > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, false > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32, false > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16, false > (m, *kp, grid, smem, st);
-	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL, false > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 0 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 0 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32, 0 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16, 0 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL, 0 > (m, *kp, grid, smem, st);
 	}
 	return (int)cudaErrorInvalidValue;
 }
 
-template < int FMT, bool DP > static cudaError_t occ_fmt(int smem, int *n)
+template < int FMT, int DP > static cudaError_t occ_fmt(int smem, int *n)
 {
 	cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	int a = 0, b = 0;
@@ -890,19 +1089,26 @@ template < int FMT, bool DP > static cudaError_t occ_fmt(int smem, int *n)
 
 extern "C" int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm)
 {
+	if (dp4a == 2) {
+		switch (fmt) {
+		case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, 2 > (smem, ctas_per_sm);
+		case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, 2 > (smem, ctas_per_sm);
+		}
+		return (int)cudaErrorInvalidValue;
+	}
 	if (dp4a) {
 		switch (fmt) {
-		case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, true > (smem, ctas_per_sm);
-		case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, true > (smem, ctas_per_sm);
+		case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, 1 > (smem, ctas_per_sm);
+		case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, 1 > (smem, ctas_per_sm);
 		}
 		return (int)cudaErrorInvalidValue;
 	}
 	switch (fmt) {
-	case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, false > (smem, ctas_per_sm);
-	case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, false > (smem, ctas_per_sm);
-	case VDL2_FMT_CF32: return (int)occ_fmt < VDL2_FMT_CF32, false > (smem, ctas_per_sm);
-	case VDL2_FMT_CS16: return (int)occ_fmt < VDL2_FMT_CS16, false > (smem, ctas_per_sm);
-	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL, false > (smem, ctas_per_sm);
+	case VDL2_FMT_CU8: return (int)occ_fmt < VDL2_FMT_CU8, 0 > (smem, ctas_per_sm);
+	case VDL2_FMT_CS8: return (int)occ_fmt < VDL2_FMT_CS8, 0 > (smem, ctas_per_sm);
+	case VDL2_FMT_CF32: return (int)occ_fmt < VDL2_FMT_CF32, 0 > (smem, ctas_per_sm);
+	case VDL2_FMT_CS16: return (int)occ_fmt < VDL2_FMT_CS16, 0 > (smem, ctas_per_sm);
+	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL, 0 > (smem, ctas_per_sm);
 	}
 	return (int)cudaErrorInvalidValue;
 }

@@ -15,6 +15,10 @@
 #define VDL2_D8_NST 3		/* per-dump TMA boxes (32 rows x 64 B) in flight per warp, integer mixer */
 #endif
 
+#ifndef VDL2_MM_NST
+#define VDL2_MM_NST 3		/* 64-byte column boxes (32 rows x 64 B) in the ring per warp, tensor-core mixer */
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
