@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VDL2_ABI_VERSION 3
+#define VDL2_ABI_VERSION 4
 
 /* input sample formats; CU8 is what rtl.c receives (rtl.c:287-289: x - 127.37f),
    CF32 is the already converted Cbuff of the reference (vdlm2.h:89),
@@ -150,6 +150,18 @@ int vdl2_destroy(vdl2gpu_t * h);
    reference carries clk/nf/no across blocks, d8psk.c:343-347) and returns when done. */
 int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes);
 
+/* The asynchronous half of vdl2_process_host(): enqueues the upload and the launch and returns; iq must stay valid (and
+   should be page-locked, vdl2_host_alloc) until vdl2_sync() or a drain.  vdl2_process_host() = vdl2_submit_host() + vdl2_sync(). */
+int vdl2_submit_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes);
+/* Same, but the samples are first copied into a page-locked ring slot owned by the handle: iq may be reused as soon as the
+   call returns.  This is what the drop-in for the reference's barrier protocol uses (Cbuff is overwritten by the next SDR
+   callback, rtl.c:283-294): the 32768-sample round costs one 256 KB memcpy and three enqueues on the host instead of a
+   synchronous pageable upload, a kernel wait and a drain. */
+int vdl2_submit_copy(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes);
+/* Number of completed blocks waiting in the queue, as of the newest launch that has FINISHED (never waits; may lag behind
+   by the launch in flight).  Lets a streaming caller skip the (synchronising) drain while nothing is pending. */
+int vdl2_pending_blocks(vdl2gpu_t * h, int *n_out);
+
 /* Device input, same layout, already resident in HBM.  Zero-copy when no tail is pending
    and nsamples is a whole number of rows; asynchronous on the handle's stream. */
 int vdl2_process_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes);
@@ -172,7 +184,7 @@ typedef struct {
 	int32_t len;		/* l: bytes in hdata including both flags */
 	int32_t chn, Fr;	/* copied from the block */
 	float ppm;
-	int32_t pad;
+	int32_t pad;		/* end_dump - sync_dump of the block: length of the burst in 84 kHz dumps */
 	int64_t sync_dump;
 	uint8_t hdata[2016];
 } vdl2_frame_t;			/* 2048 bytes */
@@ -238,6 +250,41 @@ typedef struct {
 
 /* frames (as returned by vdl2_link_decode / vdl2_drain_frames) -> one record per frame, same order */
 int vdl2_avlc_extract(vdl2gpu_t * h, const vdl2_frame_t * frames, int nframes, vdl2_avlc_t * recs);
+
+/* ---- rows f1 + f4 end to end.  Like vdl2_drain_frames(), but the frames leave the device ORDERED and PACKED: frame i is
+   hdrs[i] + bytes[hdrs[i].offset .. + hdrs[i].len) (exactly the (hdata, l) of out(), vdlm2.h:134; offsets are 16-byte
+   aligned) and, if recs != NULL, its field record recs[i] -- computed on the device before the frame left HBM.  Order =
+   completion order, the order in which the reference's single consumer sees the blocks (decodeVdlm2 at the end of a burst,
+   vdlm2.c:189-206): end of the burst (sync_dump + dur), then channel, then position inside the block.  Buffers should come
+   from vdl2_host_alloc() (page-locked); sizes: max_frames headers / records, max_bytes of frame bytes. ---- */
+typedef struct {
+	int64_t sync_dump;	/* trigger of the burst the frame came in (84 kHz dump index since create) */
+	int32_t chn, Fr;
+	float ppm;
+	int32_t len;		/* l: bytes including both flags */
+	uint32_t offset;	/* of the frame's first byte in `bytes` */
+	int32_t dur;		/* end_dump - sync_dump */
+} vdl2_frame_hdr_t;		/* 32 bytes */
+int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, int max_frames, int *n_frames, uint8_t * bytes, size_t max_bytes,
+			     size_t *n_bytes, vdl2_avlc_t * recs);
+/* device time (CUDA events) of the ranking, packing and field kernels of the last vdl2_drain_frames_packed() */
+float vdl2_last_pack_ms(const vdl2gpu_t * h);
+
+/* ---- several GPUs behind one handle: input stream s, with its channels, lives on
+   devices[s mod ndev]; there is no exchange step, so there is no collective -- every device runs the same kernel on its own
+   streams and the host merges the completed blocks into the order one device would have produced (oldest trigger first,
+   then channel), which is what the single consumer of the reference expects (blk_thread's queue, vdlm2.c:189-206).
+   cfg->device is ignored; cfg->nch / chans / the input layout are those of the WHOLE job, exactly as for vdl2_create() /
+   vdl2_process_host().  The same ordinal may appear more than once (two handles on one GPU). ---- */
+typedef struct vdl2multi vdl2multi_t;
+int vdl2_multi_create(const vdl2_config_t * cfg, const vdl2_chan_param_t * chans, const int *devices, int ndev, vdl2multi_t ** out);
+int vdl2_multi_destroy(vdl2multi_t * m);
+/* uploads and launches on every device first, then waits for all of them */
+int vdl2_multi_process_host(vdl2multi_t * m, const void *iq, size_t nsamples, size_t pitch_bytes);
+int vdl2_multi_drain_blocks(vdl2multi_t * m, vdl2_block_t * out, int max, int *n_out);
+int vdl2_multi_ndev(const vdl2multi_t * m);		/* devices that own at least one stream */
+vdl2gpu_t *vdl2_multi_handle(vdl2multi_t * m, int i);	/* the per-device handle (statistics, taps) */
+const char *vdl2_multi_last_error(const vdl2multi_t * m);	/* m may be NULL: error of the last failed create */
 
 int vdl2_get_stats(vdl2gpu_t * h, vdl2_stats_t * st);
 /* the CUDA stream the kernels run on (a cudaStream_t), so callers can bracket with events */

@@ -59,6 +59,23 @@ int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t n, size_t pitch)
 	return 0;
 }
 
+int vdl2_submit_copy(vdl2gpu_t * h, const void *iq, size_t n, size_t pitch)
+{				/* the stand-in has nothing asynchronous: the samples are consumed before the call returns */
+	return vdl2_process_host(h, iq, n, pitch);
+}
+
+int vdl2_pending_blocks(vdl2gpu_t * h, int *n_out)
+{
+	size_t total = 0;
+	for (int c = 0; c < h->cfg.nch; c++) {
+		size_t k = 0;
+		orc_tap(h->orc[c], ORC_TAP_BLOCKS, &k);
+		total += k;
+	}
+	*n_out = (int)total;
+	return 0;
+}
+
 int vdl2_process_host_rtl(vdl2gpu_t * h, const void *cu8, size_t n)
 {				/* the oracle's own statement of rtl.c:285-292, one callback at a time */
 	if (h->cfg.format != VDL2_FMT_CF32 || n % 32768 || n > h->cfg.max_samples)

@@ -35,4 +35,5 @@ def _build_checkers():
     reference mount exists (otherwise the prebuilt files that travelled with the snapshot are used)."""
     from oracle import pyoracle
     pyoracle.build("all")
+    pyoracle.build("dropin")  # the drop-in binaries of test_dropin / test_replay: never test a stale shim (no-op without /root/reference)
     yield

@@ -4,8 +4,8 @@
  *
  * It models exactly what the kernel relies on and nothing else: the 64B-swizzled TMA box layout with zero fill outside
  * the tensor, the stage ring with its W/R schedule bits, ldmatrix.x4 row addressing, the m16n8k32 fragment layouts
- * (checked on a B200 by tools/ubench/imma_ubench.cu), the B masks, the accumulator start values, the FFMA2 / shuffle
- * epilogue and the transpose tile.  tests/test_host_logic.py compares its dumps with the oracle's T1 tap, so the index
+ * (checked on a B200 by tools/ubench/imma_ubench.cu), the B masks, the accumulator start values, the FFMA2 / two-shuffle
+ * epilogue that leaves every lane with (re, im) of one row.  tests/test_host_logic.py compares its dumps with the oracle's T1 tap, so the index
  * arithmetic and the tables are pinned in the CPU tier; the GPU tier pins the kernel itself.
  */
 #include <math.h>
@@ -16,10 +16,8 @@
 #include "vdl2_common.h"
 #include "vdl2_mma_tables.h"
 
-#define MM_NST 3
+#define MM_NST 4
 #define MM_STAGE 2048
-#define MM_TPITCH 9
-#define MM_TPLANE 296
 
 namespace {
 struct Emul {
@@ -76,7 +74,6 @@ extern "C" int emul_mma_mix(const uint8_t * rows, int nrows, unsigned fs, unsign
 	E.row_bytes = row_samples * 2;
 	for (int b = 0; b < MM_NST; b++)
 		E.tma_load(b, b);
-	std::vector < float >tile(2 * MM_TPLANE, 0.f);
 	int st = 0, box = 0;
 	E.stage_waited[0] = true;	/* the wait in front of the loop */
 	for (int dk = 0; dk < ND; dk++) {
@@ -179,30 +176,29 @@ extern "C" int emul_mma_mix(const uint8_t * rows, int nrows, unsigned fs, unsign
 				p[lane][q] = yx + yy;
 			}
 		}
+		float v[32][2];
 		for (int lane = 0; lane < 32; lane++) {
-			const int g = lane >> 2, t = lane & 3;
+			const int t = lane & 3;
 			const bool odd = t & 1;
 			const float r0 = odd ? p[lane ^ 1][2] : p[lane ^ 1][0];	/* what the partner sends: odd ? p[0] : p[2] of the PARTNER */
 			const float r1 = odd ? p[lane ^ 1][3] : p[lane ^ 1][1];
 			const Vdl2MmaI4 dc = dt[dk * 4 + t];
 			const float sf = as_float(dc.z), corr = as_float(dc.w);
-			float *tw = tile.data() + (t >> 1) * MM_TPLANE + (g + 16 * (t & 1)) * MM_TPITCH;
-			tw[dk & 7] = fmaf((odd ? p[lane][2] : p[lane][0]) + r0, sf, corr);
-			tw[8 * MM_TPITCH + (dk & 7)] = fmaf((odd ? p[lane][3] : p[lane][1]) + r1, sf, corr);
+			v[lane][0] = fmaf((odd ? p[lane][2] : p[lane][0]) + r0, sf, corr);
+			v[lane][1] = fmaf((odd ? p[lane][3] : p[lane][1]) + r1, sf, corr);
+		}
+		for (int lane = 0; lane < 32; lane++) {
+			const int g = lane >> 2, t = lane & 3, hi = t >> 1;
+			const float rx = hi ? v[lane ^ 2][1] : v[lane ^ 2][0];	/* the partner sends hi ? v0 : v1 of ITS hi */
+			const int row = g + 16 * (t & 1) + 8 * hi;
+			out[((size_t) row * ND + dk) * 2] = hi ? rx : v[lane][0];
+			out[((size_t) row * ND + dk) * 2 + 1] = hi ? v[lane][1] : rx;
 		}
 		if (sk & VDL2_MM_R) {
 			if (box + MM_NST < nbox)
 				E.tma_load(st, box + MM_NST);
 			box++;
 			st = st1;
-		}
-		if ((dk & 7) == 7 || dk == ND - 1) {
-			const int k0 = dk & ~7, ng = dk - k0 + 1;
-			for (int r = 0; r < 32; r++)
-				for (int col = 0; col < ng; col++) {
-					out[((size_t) r * ND + k0 + col) * 2] = tile[r * MM_TPITCH + col];
-					out[((size_t) r * ND + k0 + col) * 2 + 1] = tile[MM_TPLANE + r * MM_TPITCH + col];
-				}
 		}
 	}
 	/* every box issued must have been waited for exactly once: the kernel's barrier phase bits rely on it */

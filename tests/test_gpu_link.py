@@ -117,3 +117,39 @@ def test_link_full_size_round_trip(gpu):
     for i in range(0, len(f), 97):
         assert bytes(f[i]["hdata"][:f[i]["len"]]) == want[i % 256]
     assert np.array_equal(f["len"], np.array([len(w) for w in want] * 64))
+
+
+def test_drain_frames_packed_equals_records_and_port(tmp_path):
+    """Rows f1 + f4 end to end (vdl2_drain_frames_packed): ACARS-over-AVLC bursts on 4 channels of one stream -> the frames leave
+    the device ordered (completion order) and packed, with their field records.  Bytes must equal the fixed-record drain of a
+    second handle, records must equal the port's walk of the same frames, the order must be (end of burst, channel, length)."""
+    from oracle import pyoracle
+    from tests.test_dropin import _capture
+    fos = [-50_000, -175_000, -300_000, 125_000]
+    cap, nb = _capture(tmp_path, fos, nblk=40, seed=9, acars=True)
+    iq = np.fromfile(cap, dtype=np.uint8)[None, :]
+    n = iq.shape[1] // 2
+    chans = [(c, 136_975_000 + fo + 50_000, fo) for c, fo in enumerate(fos)]
+    a = Vdl2Gpu(chans, ch_per_stream=len(fos), max_samples=n)
+    a.process(iq)
+    frames, blocks = a.drain_frames()
+    b = Vdl2Gpu(chans, ch_per_stream=len(fos), max_samples=n)
+    b.process(iq)
+    hdrs, data, recs = b.drain_frames_packed()
+    assert len(hdrs) == len(frames) >= nb // 2 > 4
+    end = hdrs["sync_dump"] + hdrs["dur"]
+    key = list(zip(end.tolist(), hdrs["chn"].tolist(), hdrs["len"].tolist()))
+    assert key == sorted(key), "packed frames are not in completion order"
+    assert (hdrs["offset"] % 16 == 0).all() and len(data) == int(((hdrs["len"] + 15) // 16 * 16).sum())
+    # same frames as the fixed-record drain (which orders by trigger time)
+    want = {(int(f["sync_dump"]), int(f["chn"]), int(f["len"])): bytes(f["hdata"][:f["len"]]) for f in frames}
+    durs = {(int(x["sync_dump"]), int(x["chn"])): int(x["end_dump"] - x["sync_dump"]) for x in blocks}
+    for h in hdrs:
+        k = (int(h["sync_dump"]), int(h["chn"]), int(h["len"]))
+        assert bytes(data[h["offset"]:h["offset"] + h["len"]]) == want[k]
+        assert durs[k[:2]] == h["dur"]
+    # field records: the port's walk of the same frames, in the same order
+    port = np.array([pyoracle.avlc_extract(bytes(data[h["offset"]:h["offset"] + h["len"]])) for h in hdrs], dtype=pyoracle.AVLC_DT)
+    assert recs.tobytes() == port.tobytes()
+    assert (recs["kind"] == 2).sum() >= len(hdrs) // 2      # well-formed ACARS bodies: the lane-parallel CRC says good
+    assert b.last_pack_ms > 0 and len(b.drain_frames_packed()[0]) == 0

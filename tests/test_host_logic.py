@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = api.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vdl2_abi_version() == 3
+    assert lib.vdl2_abi_version() == 4
 
 
 def test_no_gpu_means_loud_failure():
@@ -47,7 +47,7 @@ def test_struct_layouts_match_header():
     assert api.BLKSTAT_DT.itemsize == 16 and api.BLKSTAT_DT == pyoracle.BLKSTAT_DT
     assert api.AVLC_DT.itemsize == 48 and api.AVLC_DT == pyoracle.AVLC_DT and api.AVLC_DT.fields["txt_off"][1] == 40  # vdl2_avlc_t (row f4)
     hdr = open(os.path.join(ROOT, "include", "vdl2gpu.h")).read()
-    assert "uint8_t hdata[2016];" in hdr and "} vdl2_frame_t;" in hdr and "#define VDL2_ABI_VERSION 3" in hdr
+    assert "uint8_t hdata[2016];" in hdr and "} vdl2_frame_t;" in hdr and "#define VDL2_ABI_VERSION 4" in hdr
 
 
 @pytest.mark.parametrize("tile", [2688, 84, 84 * 5, 1000])

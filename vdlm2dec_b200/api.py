@@ -46,6 +46,9 @@ AVLC_DT = np.dtype([("faddr", "<u4"), ("taddr", "<u4"), ("fromair", "u1"), ("rep
                     ("nno", "u1"), ("nfid", "u1"), ("no", "u1", (4,)), ("fid", "u1", (6,)), ("pad", "u1"),
                     ("txt_off", "<u2"), ("txt_len", "<u2"), ("info_off", "<u2"), ("info_len", "<u2")])
 assert AVLC_DT.itemsize == 48
+# vdl2_frame_hdr_t: header of a packed frame (vdl2_drain_frames_packed)
+FRAME_HDR_DT = np.dtype([("sync_dump", "<i8"), ("chn", "<i4"), ("Fr", "<i4"), ("ppm", "<f4"), ("len", "<i4"), ("offset", "<u4"), ("dur", "<i4")])
+assert FRAME_HDR_DT.itemsize == 32
 
 
 class ChanParam(C.Structure):  # thread_param_t, vdlm2.h:49-52
@@ -68,7 +71,10 @@ class Stats(C.Structure):
 EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy", "vdl2_process_host",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
            "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
-           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl", "vdl2_avlc_extract"]
+           "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl", "vdl2_avlc_extract",
+           "vdl2_submit_host", "vdl2_submit_copy", "vdl2_pending_blocks", "vdl2_drain_frames_packed", "vdl2_last_pack_ms",
+           "vdl2_multi_create", "vdl2_multi_destroy", "vdl2_multi_process_host", "vdl2_multi_drain_blocks", "vdl2_multi_ndev",
+           "vdl2_multi_handle", "vdl2_multi_last_error"]
 
 _lib = None
 
@@ -89,6 +95,22 @@ def load_library():
     lib.vdl2_destroy.argtypes = [C.c_void_p]
     lib.vdl2_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     lib.vdl2_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_submit_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_pending_blocks.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.vdl2_drain_frames_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t,
+                                             C.POINTER(C.c_size_t), C.c_void_p]
+    lib.vdl2_last_pack_ms.restype = C.c_float
+    lib.vdl2_last_pack_ms.argtypes = [C.c_void_p]
+    lib.vdl2_multi_create.argtypes = [C.POINTER(Config), C.POINTER(ChanParam), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    lib.vdl2_multi_destroy.argtypes = [C.c_void_p]
+    lib.vdl2_multi_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.vdl2_multi_drain_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.vdl2_multi_ndev.argtypes = [C.c_void_p]
+    lib.vdl2_multi_handle.restype = C.c_void_p
+    lib.vdl2_multi_handle.argtypes = [C.c_void_p, C.c_int]
+    lib.vdl2_multi_last_error.restype = C.c_char_p
+    lib.vdl2_multi_last_error.argtypes = [C.c_void_p]
     lib.vdl2_sync.argtypes = [C.c_void_p]
     lib.vdl2_drain_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     for f in ("vdl2_read_dumps", "vdl2_read_steps", "vdl2_read_syncs", "vdl2_read_syms"):
@@ -170,6 +192,20 @@ class Vdl2Gpu:
     def process_ptr(self, host_ptr: int, nsamples: int, pitch_bytes: int):
         self._check(self.lib.vdl2_process_host(self.h, C.c_void_p(host_ptr), nsamples, pitch_bytes))
 
+    def submit_copy(self, iq: np.ndarray):
+        """Asynchronous ingest: the samples are copied into a page-locked ring slot of the handle and the upload + launch are
+        enqueued; returns at once, `iq` may be reused.  Collect with pending_blocks() / drain_blocks()."""
+        iq = np.ascontiguousarray(iq, dtype=FMT_DTYPE[self.fmt])
+        if iq.ndim == 1:
+            iq = iq.reshape(1, -1)
+        row_bytes = iq.shape[1] * iq.itemsize
+        self._check(self.lib.vdl2_submit_copy(self.h, iq.ctypes.data_as(C.c_void_p), row_bytes // self.bps, row_bytes))
+
+    def pending_blocks(self) -> int:
+        n = C.c_int(0)
+        self._check(self.lib.vdl2_pending_blocks(self.h, C.byref(n)))
+        return n.value
+
     def process_device(self, dev_ptr: int, nsamples: int, pitch_bytes: int):
         """Device-resident input (e.g. a torch tensor's data_ptr()); asynchronous, see sync()."""
         self._check(self.lib.vdl2_process_device(self.h, C.c_void_p(dev_ptr), nsamples, pitch_bytes))
@@ -214,6 +250,28 @@ class Vdl2Gpu:
                                                blocks.ctypes.data_as(C.c_void_p), len(blocks), C.byref(nb)))
         return frames[:nf.value].copy(), blocks[:nb.value].copy()
 
+    def drain_frames_packed(self, want_records: bool = True, max_frames: int | None = None):
+        """Rows f1 + f4 end to end: (headers, packed frame bytes, field records or None), completion order; page-locked buffers
+        owned by the handle (allocated once with vdl2_host_alloc)."""
+        nf_cap = max_frames or max(2 * self._cap_blocks, 16)
+        if getattr(self, "_pk", None) is None or self._pk[0] < nf_cap:
+            def pinned(nbytes, dt):
+                p = C.c_void_p()
+                if self.lib.vdl2_host_alloc(nbytes, C.byref(p)):
+                    raise Vdl2Error(self.lib.vdl2_last_error(None).decode())
+                buf = (C.c_char * nbytes).from_address(p.value)
+                return np.frombuffer(buf, dtype=dt)
+            self._pk = (nf_cap, pinned(32 * nf_cap, FRAME_HDR_DT), pinned(512 * nf_cap, np.uint8), pinned(48 * nf_cap, AVLC_DT))
+        _, hdrs, data, recs = self._pk
+        nf, nb = C.c_int(0), C.c_size_t(0)
+        self._check(self.lib.vdl2_drain_frames_packed(self.h, hdrs.ctypes.data_as(C.c_void_p), nf_cap, C.byref(nf), data.ctypes.data_as(C.c_void_p),
+                                                      data.nbytes, C.byref(nb), recs.ctypes.data_as(C.c_void_p) if want_records else None))
+        return hdrs[:nf.value], data[:nb.value], (recs[:nf.value] if want_records else None)
+
+    @property
+    def last_pack_ms(self) -> float:
+        return float(self.lib.vdl2_last_pack_ms(self.h))
+
     def _read(self, fn, ch, dt, cap):
         out = np.zeros(cap, dtype=dt)
         n = C.c_size_t(0)
@@ -244,3 +302,60 @@ class Vdl2Gpu:
     @property
     def cuda_stream(self) -> int:
         return int(self.lib.vdl2_cuda_stream(self.h) or 0)
+
+
+class Vdl2Multi:
+    """Several GPUs behind one handle (vdl2_multi_*, include/vdl2gpu.h): stream s with its channels lives on devices[s mod N],
+    no collective; completed blocks come back merged in the order one GPU would have produced them."""
+
+    def __init__(self, chans: Sequence[tuple[int, int, int]], devices: Sequence[int], fs: int = 2_000_000, sdrclk: int = 500,
+                 fmt: str = "cu8", ch_per_stream: int = 1, taps: int = 0, max_samples: int = 1 << 22, max_blocks: int = 0):
+        self.lib = load_library()
+        self.fmt = fmt
+        self.nch = len(chans)
+        self.nstreams = self.nch // ch_per_stream
+        self.bps = FMT_BYTES[fmt]
+        arr = (ChanParam * self.nch)(*[ChanParam(*c) for c in chans])
+        dev = (C.c_int * len(devices))(*devices)
+        cfg = Config(fs, sdrclk, FORMATS[fmt], self.nch, ch_per_stream, 0, taps, max_samples, max_blocks)
+        self.h = C.c_void_p()
+        if self.lib.vdl2_multi_create(C.byref(cfg), arr, dev, len(devices), C.byref(self.h)):
+            raise Vdl2Error(self.lib.vdl2_multi_last_error(None).decode())
+        self._cap_blocks = (max_blocks if max_blocks > 0 else max(4096, self.nch * 8)) * len(devices)
+
+    def _check(self, rc):
+        if rc:
+            raise Vdl2Error(self.lib.vdl2_multi_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vdl2_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ndev(self) -> int:
+        return self.lib.vdl2_multi_ndev(self.h)
+
+    def process(self, iq: np.ndarray):
+        iq = np.ascontiguousarray(iq, dtype=FMT_DTYPE[self.fmt])
+        if iq.ndim == 1:
+            iq = iq.reshape(1, -1)
+        assert iq.shape[0] == self.nstreams, (iq.shape, self.nstreams)
+        row_bytes = iq.shape[1] * iq.itemsize
+        self._check(self.lib.vdl2_multi_process_host(self.h, iq.ctypes.data_as(C.c_void_p), row_bytes // self.bps, row_bytes))
+        return self
+
+    def process_ptr(self, host_ptr: int, nsamples: int, pitch_bytes: int):
+        self._check(self.lib.vdl2_multi_process_host(self.h, C.c_void_p(host_ptr), nsamples, pitch_bytes))
+
+    def drain_blocks(self) -> np.ndarray:
+        out = np.zeros(self._cap_blocks, dtype=BLOCK_DT)
+        n = C.c_int(0)
+        self._check(self.lib.vdl2_multi_drain_blocks(self.h, out.ctypes.data_as(C.c_void_p), len(out), C.byref(n)))
+        return out[:n.value].copy()

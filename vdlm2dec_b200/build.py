@@ -11,8 +11,8 @@ LIB = os.path.join(HERE, "libvdl2gpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
-SOURCES = ["vdl2_kernel.cu", "vdl2_link.cu", "vdl2_avlc.cu", "vdl2_host.cu"]
-HEADERS = ["vdl2_kernel.h", "vdl2_link.h", "vdl2_common.h", "vdl2_demod.cuh", "vdl2_avlc.cuh", "vdl2_tables.h", os.path.join("..", "..", "include", "vdl2gpu.h")]
+SOURCES = ["vdl2_kernel.cu", "vdl2_link.cu", "vdl2_avlc.cu", "vdl2_host.cu", "vdl2_multi.cu"]
+HEADERS = ["vdl2_kernel.h", "vdl2_link.h", "vdl2_common.h", "vdl2_demod.cuh", "vdl2_avlc.cuh", "vdl2_tables.h", "vdl2_mma_tables.h", os.path.join("..", "..", "include", "vdl2gpu.h")]
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -5,8 +5,9 @@
  *   out.c:562-570   payload class: XID group (0x82), ACARS (ff ff 01), other, none
  *   outacars.c:214-290  ACARS: CRC over the body, parity strip, mode, registration, ack, label, block id, message number,
  *                   flight id, text extent, end-of-block character
- * Formatting (fixreg, label decoding, text, JSON) stays on the host.  One scalar walk per frame; the same source is compiled
- * for the device (vdl2_avlc.cu, a warp stages the frame in shared memory, lane 0 walks it) and for the host test build
+ * Formatting (fixreg, label decoding, text, JSON) stays on the host.  The same source is compiled for the device
+ * (vdl2_avlc.cu: a warp stages the frame in shared memory, computes the ACARS CRC lane-parallel -- it is linear -- and lane 0
+ * walks the handful of header fields) and for the host test build
  * (tests/emul), where it is compared byte for byte with the oracle's independent port.
  */
 #ifndef VDL2_AVLC_CUH
@@ -14,7 +15,7 @@
 #include <stdint.h>
 
 #ifdef __CUDACC__
-#define VDL2_AVLC_FN __device__ __forceinline__
+#define VDL2_AVLC_FN __host__ __device__ __forceinline__
 #else
 #define VDL2_AVLC_FN static inline
 #endif
@@ -61,7 +62,15 @@ VDL2_AVLC_FN uint32_t avlc_crc(uint32_t crc, uint32_t c)
 	return ((crc >> 8) ^ (d << 8) ^ (d << 3) ^ (d >> 4)) & 0xffffu;
 }
 
-VDL2_AVLC_FN void avlc_extract(const uint8_t * h, int l, Vdl2AvlcRec * r)
+/* does the frame carry an ACARS body whose CRC has to be computed?  (out.c:566: ff ff 01 in front of it) */
+VDL2_AVLC_FN bool avlc_is_acars(const uint8_t * h, int l)
+{
+	return l >= 16 && h[10] != 0x82 && h[10] == 0xff && h[11] == 0xff && h[12] == 0x01;
+}
+
+/* the field walk proper.  `crc` = CRC over the ACARS body t[0 .. n-2] (outacars.c:222-230), used only when avlc_is_acars();
+   the device computes it lane-parallel (vdl2_avlc.cu), the host build and single-lane callers through avlc_extract() below */
+VDL2_AVLC_FN void avlc_fields(const uint8_t * h, int l, uint32_t crc, Vdl2AvlcRec * r)
 {
 	Vdl2AvlcRec o;
 	o.faddr = avlc_addr(h + 5);
@@ -90,9 +99,6 @@ VDL2_AVLC_FN void avlc_extract(const uint8_t * h, int l, Vdl2AvlcRec * r)
 		else if (l >= 16 && h[10] == 0xff && h[11] == 0xff && h[12] == 0x01) {
 			const uint8_t *t = h + 13;
 			const int n = l - 16;	/* body, two CRC octets, DEL */
-			uint32_t crc = 0;
-			for (int i = 0; i < n - 1; i++)
-				crc = avlc_crc(crc, t[i]);
 			o.kind = crc ? AVLC_ACARS_BADCRC : AVLC_ACARS;
 			if (!crc) {
 				/* octets 0 .. n-2 lose their parity bit (outacars.c:223-226); anything at or beyond n-1 is only
@@ -134,5 +140,14 @@ VDL2_AVLC_FN void avlc_extract(const uint8_t * h, int l, Vdl2AvlcRec * r)
 			o.kind = AVLC_OTHER;
 	}
 	*r = o;
+}
+
+VDL2_AVLC_FN void avlc_extract(const uint8_t * h, int l, Vdl2AvlcRec * r)
+{
+	uint32_t crc = 0;
+	if (avlc_is_acars(h, l))
+		for (int i = 0; i < l - 16 - 1; i++)
+			crc = avlc_crc(crc, h[13 + i]);
+	avlc_fields(h, l, crc, r);
 }
 #endif

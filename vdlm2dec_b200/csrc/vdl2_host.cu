@@ -35,6 +35,8 @@ static_assert(sizeof(Vdl2SymRec) == sizeof(vdl2_sym_t), "sym record layout");
 static_assert(sizeof(Vdl2FrameRec) == sizeof(vdl2_frame_t) && sizeof(vdl2_frame_t) == 2048, "frame record layout");
 static_assert(sizeof(Vdl2BlkStat) == sizeof(vdl2_blkstat_t), "block statistics layout");
 
+#define VDL2_PIN_SLOTS 4
+#define VDL2_MIRROR_SLOTS 8	/* > VDL2_PIN_SLOTS: a vdl2_submit_copy() caller is never more launches ahead of the device than the ring is deep */
 static thread_local std::string g_create_error;
 
 struct vdl2gpu {
@@ -91,8 +93,26 @@ struct vdl2gpu {
 	bool lev_valid, link_ready;
 	void *d_avlc;		/* field records of one vdl2_avlc_extract() call, grown on demand */
 	int avlc_cap;
+	/* packed drain (vdl2_drain_frames_packed): rank / offsets / headers / bytes / records on the device, totals in page-locked memory */
+	int *d_rank;
+	unsigned *d_offs, *d_totals;
+	void *d_hdrs, *d_precs;
+	uint8_t *d_pbytes;
+	int pack_cap;
+	unsigned *h_totals;
+	cudaEvent_t pev0, pev1;
+	float last_pack_ms;
 	uint8_t *d_raw;		/* raw cu8 bytes of one vdl2_process_host_rtl() call, grown on demand */
 	size_t raw_cap;
+	/* asynchronous ingest (vdl2_submit_copy): ring of page-locked slots the caller's buffer is copied into, one event per slot
+	   (recorded behind the slot's upload); mirror of the device counters in page-locked host memory, refreshed behind every launch */
+	uint8_t *pin[VDL2_PIN_SLOTS];
+	cudaEvent_t pin_ev[VDL2_PIN_SLOTS];
+	size_t pin_bytes;
+	unsigned pin_next;
+	unsigned *h_mirror;	/* [VDL2_MIRROR_SLOTS][16] copies of d_ticket, one slot per launch in turn */
+	cudaEvent_t mirror_ev[VDL2_MIRROR_SLOTS];
+	unsigned mirror_seq;	/* launches whose mirror copy was enqueued */
 };
 
 static int fail(vdl2gpu * h, const char *fmt, ...)
@@ -625,6 +645,29 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_lstats);
 	cudaFree(h->d_lrows);
 	cudaFree(h->d_nframes);
+	cudaFree(h->d_rank);
+	cudaFree(h->d_offs);
+	cudaFree(h->d_totals);
+	cudaFree(h->d_hdrs);
+	cudaFree(h->d_precs);
+	cudaFree(h->d_pbytes);
+	if (h->h_totals)
+		cudaFreeHost(h->h_totals);
+	if (h->pev0)
+		cudaEventDestroy(h->pev0);
+	if (h->pev1)
+		cudaEventDestroy(h->pev1);
+	for (int i = 0; i < VDL2_PIN_SLOTS; i++) {
+		if (h->pin[i])
+			cudaFreeHost(h->pin[i]);
+		if (h->pin_ev[i])
+			cudaEventDestroy(h->pin_ev[i]);
+	}
+	if (h->h_mirror)
+		cudaFreeHost(h->h_mirror);
+	for (int i = 0; i < VDL2_MIRROR_SLOTS; i++)
+		if (h->mirror_ev[i])
+			cudaEventDestroy(h->mirror_ev[i]);
 	if (h->link_ready) {
 		cudaEventDestroy(h->lev0);
 		cudaEventDestroy(h->lev1);
@@ -736,6 +779,12 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 		CK(h, cudaEventRecord(h->ev1, h->stream));
 		h->ev_valid = true;
 	}
+	if (h->h_mirror) {	/* somebody polls (vdl2_pending_blocks): refresh the host mirror of the counters behind this launch */
+		const unsigned q = h->mirror_seq % VDL2_MIRROR_SLOTS;
+		CK(h, cudaMemcpyAsync(h->h_mirror + 16 * q, h->d_ticket, 64, cudaMemcpyDeviceToHost, h->stream));
+		CK(h, cudaEventRecord(h->mirror_ev[q], h->stream));
+		h->mirror_seq++;
+	}
 	h->launch_seq++;
 	h->tiles_done += kp.ntiles;
 	h->st.kernel_launches++;
@@ -761,23 +810,94 @@ static int run_staged(vdl2gpu * h, size_t total)
 	return 0;
 }
 
-extern "C" int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes)
+extern "C" int vdl2_submit_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes)
 {
 	if (!h || !iq)
-		return fail(h, "vdl2_process_host: null argument");
+		return fail(h, "vdl2_submit_host: null argument");
 	CK(h, cudaSetDevice(h->cfg.device));
 	const size_t bps = h->bytes_per_sample;
 	if ((h->carry + nsamples) * bps > h->stage_pitch)
-		return fail(h, "vdl2_process_host: %zu samples exceed max_samples of the handle", nsamples);
+		return fail(h, "vdl2_submit_host: %zu samples exceed max_samples of the handle", nsamples);
 	if (h->nstreams > 1 && pitch_bytes < nsamples * bps)
-		return fail(h, "vdl2_process_host: pitch %zu smaller than a stream (%zu bytes)", pitch_bytes, nsamples * bps);
+		return fail(h, "vdl2_submit_host: pitch %zu smaller than a stream (%zu bytes)", pitch_bytes, nsamples * bps);
 	h->st.samples_in += nsamples;
 	if (nsamples)
 		CK(h, cudaMemcpy2DAsync(h->d_stage + h->carry * bps, h->stage_pitch, iq, h->nstreams > 1 ? pitch_bytes : nsamples * bps,
 					nsamples * bps, h->nstreams, cudaMemcpyHostToDevice, h->stream));
-	if (run_staged(h, h->carry + nsamples))
+	return run_staged(h, h->carry + nsamples);
+}
+
+extern "C" int vdl2_process_host(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes)
+{
+	if (vdl2_submit_host(h, iq, nsamples, pitch_bytes))
 		return 1;
 	CK(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+/* the caller's buffer is copied into a page-locked ring slot first, so it may be reused as soon as the call returns (the
+   reference's Cbuff is overwritten by the next SDR callback, rtl.c:283-294) and the upload runs at the PCIe rate */
+extern "C" int vdl2_submit_copy(vdl2gpu_t * h, const void *iq, size_t nsamples, size_t pitch_bytes)
+{
+	if (!h || !iq)
+		return fail(h, "vdl2_submit_copy: null argument");
+	CK(h, cudaSetDevice(h->cfg.device));
+	const size_t bps = h->bytes_per_sample, row = nsamples * bps;
+	if (h->nstreams > 1 && pitch_bytes < row)
+		return fail(h, "vdl2_submit_copy: pitch %zu smaller than a stream (%zu bytes)", pitch_bytes, row);
+	const size_t need = row * h->nstreams;
+	if (need > h->pin_bytes) {	/* first use, or a larger call than before: (re)build the ring */
+		CK(h, cudaStreamSynchronize(h->stream));
+		for (int i = 0; i < VDL2_PIN_SLOTS; i++) {
+			if (h->pin[i])
+				cudaFreeHost(h->pin[i]);
+			h->pin[i] = NULL;
+		}
+		h->pin_bytes = 0;
+		for (int i = 0; i < VDL2_PIN_SLOTS; i++) {
+			CK(h, cudaHostAlloc((void **)&h->pin[i], need, cudaHostAllocPortable));
+			if (!h->pin_ev[i])
+				CK(h, cudaEventCreateWithFlags(&h->pin_ev[i], cudaEventDisableTiming));
+		}
+		h->pin_bytes = need;
+	}
+	const unsigned slot = h->pin_next++ % VDL2_PIN_SLOTS;
+	CK(h, cudaEventSynchronize(h->pin_ev[slot]));	/* the upload that last used this slot (a never-recorded event is complete) */
+	for (int s_ = 0; s_ < h->nstreams; s_++)
+		memcpy(h->pin[slot] + (size_t) s_ * row, (const uint8_t *)iq + (size_t) s_ * pitch_bytes, row);
+	if (vdl2_submit_host(h, h->pin[slot], nsamples, row))
+		return 1;
+	CK(h, cudaEventRecord(h->pin_ev[slot], h->stream));
+	return 0;
+}
+
+/* blocks completed by launches that have FINISHED, without waiting for one that is still running (may lag by one launch) */
+extern "C" int vdl2_pending_blocks(vdl2gpu_t * h, int *n_out)
+{
+	if (!h || !n_out)
+		return fail(h, "vdl2_pending_blocks: null argument");
+	*n_out = 0;
+	CK(h, cudaSetDevice(h->cfg.device));
+	if (!h->h_mirror) {	/* first poll: from now on every launch refreshes the mirror */
+		CK(h, cudaHostAlloc((void **)&h->h_mirror, VDL2_MIRROR_SLOTS * 64, cudaHostAllocPortable));
+		memset(h->h_mirror, 0, VDL2_MIRROR_SLOTS * 64);
+		for (int i = 0; i < VDL2_MIRROR_SLOTS; i++)
+			CK(h, cudaEventCreateWithFlags(&h->mirror_ev[i], cudaEventDisableTiming));
+		CK(h, cudaMemcpyAsync(h->h_mirror, h->d_ticket, 64, cudaMemcpyDeviceToHost, h->stream));
+		CK(h, cudaEventRecord(h->mirror_ev[0], h->stream));
+		h->mirror_seq = 1;
+	}
+	/* newest mirror whose copy has completed */
+	for (unsigned back = 1; back <= VDL2_MIRROR_SLOTS && back <= h->mirror_seq; back++) {
+		const unsigned q = (h->mirror_seq - back) % VDL2_MIRROR_SLOTS;
+		const cudaError_t e = cudaEventQuery(h->mirror_ev[q]);
+		if (e == cudaSuccess) {
+			*n_out = (int)std::min(h->h_mirror[16 * q + 4], h->outq_cap);
+			return 0;
+		}
+		if (e != cudaErrorNotReady)
+			return fail(h, "vdl2_pending_blocks: %s", cudaGetErrorString(e));
+	}
 	return 0;
 }
 
@@ -906,6 +1026,9 @@ extern "C" int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int
 	CK(h, cudaMemset(h->d_outq_count, 0, 4));
 	if (cnt[4])
 		CK(h, cudaMemset(h->d_dropped, 0, 4));
+	if (h->h_mirror)	/* the stream is idle: no mirror copy is in flight */
+		for (int i = 0; i < VDL2_MIRROR_SLOTS; i++)
+			h->h_mirror[16 * i + 4] = 0;
 	sort_records(out, (size_t) n,[](const vdl2_block_t & a, const vdl2_block_t & b) {
 		     return a.sync_dump != b.sync_dump ? a.sync_dump < b.sync_dump : a.chn < b.chn;}
 	);
@@ -1059,6 +1182,9 @@ extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_f
 	if (link_run(h, h->d_outq, (int)n, frames, max_frames, n_frames, false))
 		return 1;
 	CK(h, cudaMemsetAsync(h->d_outq_count, 0, 4, h->stream));
+	if (h->h_mirror)
+		for (int i = 0; i < VDL2_MIRROR_SLOTS; i++)
+			h->h_mirror[16 * i + 4] = 0;
 	if (blocks) {
 		/* order of the blocks: oldest trigger first (the order drain_blocks returns); frame.block follows it */
 		std::vector < vdl2_block_t > q(n);
@@ -1087,6 +1213,109 @@ extern "C" int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_f
 	if (n_blocks)
 		*n_blocks = (int)n;
 	return 0;
+}
+
+/* ---- rows f1 + f4 end to end: the completed blocks never leave the device as blocks.  Block pipeline -> frames, ranked in
+   completion order, packed (32-byte header + the frame's own bytes, 16-byte aligned) with their field records, three small
+   asynchronous copies.  The fixed 2048-byte records of vdl2_drain_frames() cost 9 MB of synchronous pageable copy and a host
+   sort per bench step (26-52 ms); this is a few hundred microseconds. ---- */
+extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, int max_frames, int *n_frames, uint8_t * bytes, size_t max_bytes,
+					size_t *n_bytes, vdl2_avlc_t * recs)
+{
+	if (!h || !n_frames || !n_bytes || !hdrs || !bytes)
+		return fail(h, "vdl2_drain_frames_packed: null argument");
+	static_assert(sizeof(vdl2_frame_hdr_t) == 32, "frame header layout");
+	*n_frames = 0;
+	*n_bytes = 0;
+	CK(h, cudaSetDevice(h->cfg.device));
+	CK(h, cudaStreamSynchronize(h->stream));
+	unsigned cnt[8];
+	CK(h, cudaMemcpy(cnt, h->d_outq_count, sizeof cnt, cudaMemcpyDeviceToHost));
+	const unsigned n = std::min(cnt[0], h->outq_cap);
+	h->st.blocks_dropped += cnt[4];
+	if (cnt[4])
+		CK(h, cudaMemset(h->d_dropped, 0, 4));
+	if (n == 0)
+		return 0;
+	const int fcap = std::max(max_frames, 256);
+	if (link_reserve(h, (int)n, fcap, false))
+		return 1;
+	if (fcap > h->pack_cap) {
+		cudaFree(h->d_rank);
+		cudaFree(h->d_offs);
+		cudaFree(h->d_hdrs);
+		cudaFree(h->d_precs);
+		cudaFree(h->d_pbytes);
+		h->d_rank = NULL;
+		h->d_offs = NULL;
+		h->d_hdrs = h->d_precs = NULL;
+		h->d_pbytes = NULL;
+		h->pack_cap = 0;
+		CK(h, cudaMalloc(&h->d_rank, sizeof(int) * (size_t) fcap));
+		CK(h, cudaMalloc(&h->d_offs, sizeof(unsigned) * (size_t) fcap));
+		CK(h, cudaMalloc(&h->d_hdrs, 32 * (size_t) fcap));
+		CK(h, cudaMalloc(&h->d_precs, sizeof(vdl2_avlc_t) * (size_t) fcap));
+		CK(h, cudaMalloc(&h->d_pbytes, (size_t) 2032 * fcap));	/* worst case: every frame 2016 bytes + padding */
+		h->pack_cap = fcap;
+	}
+	if (!h->d_totals) {
+		CK(h, cudaMalloc(&h->d_totals, 16));
+		CK(h, cudaHostAlloc((void **)&h->h_totals, 16, cudaHostAllocPortable));
+		CK(h, cudaEventCreate(&h->pev0));
+		CK(h, cudaEventCreate(&h->pev1));
+	}
+	const unsigned cap = (unsigned)std::min(fcap, h->lcap_frames);
+	CK(h, cudaMemsetAsync(h->d_nframes, 0, 4, h->stream));
+	CK(h, cudaEventRecord(h->lev0, h->stream));
+	cudaError_t e = (cudaError_t) vdl2_link_launch(h->d_outq, (int)n, h->d_frames, h->d_nframes, cap, h->d_lstats, NULL, h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "block pipeline launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaEventRecord(h->lev1, h->stream));
+	h->lev_valid = true;
+	h->st.link_launches++;
+	CK(h, cudaEventRecord(h->pev0, h->stream));
+	e = (cudaError_t) vdl2_frames_pack_launch(h->d_frames, h->d_nframes, cap, h->d_rank, h->d_offs, h->d_totals, h->d_hdrs, h->d_pbytes,
+						  (unsigned)std::min < size_t > ((size_t) 2032 * h->pack_cap, 0xffffffffu), recs ? h->d_precs : NULL,
+						  (int)std::min < unsigned >(4 * n, cap), h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "frame packing launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaEventRecord(h->pev1, h->stream));
+	CK(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 8, cudaMemcpyDeviceToHost, h->stream));
+	CK(h, cudaMemsetAsync(h->d_outq_count, 0, 4, h->stream));
+	CK(h, cudaStreamSynchronize(h->stream));
+	if (h->h_mirror)
+		for (int i = 0; i < VDL2_MIRROR_SLOTS; i++)
+			h->h_mirror[16 * i + 4] = 0;
+	h->st.blocks_out += n;
+	const unsigned nf = h->h_totals[0], nb = h->h_totals[1];
+	unsigned raw = 0;
+	CK(h, cudaMemcpy(&raw, h->d_nframes, 4, cudaMemcpyDeviceToHost));
+	if (raw > cap || (int)nf > max_frames)
+		return fail(h, "vdl2_drain_frames_packed: %u frames, room for %d", raw, std::min(max_frames, (int)cap));
+	if (nb > max_bytes)
+		return fail(h, "vdl2_drain_frames_packed: %u bytes of frames, room for %zu", nb, max_bytes);
+	if (nf) {
+		CK(h, cudaMemcpyAsync(hdrs, h->d_hdrs, 32 * (size_t) nf, cudaMemcpyDeviceToHost, h->stream));
+		CK(h, cudaMemcpyAsync(bytes, h->d_pbytes, nb, cudaMemcpyDeviceToHost, h->stream));
+		if (recs)
+			CK(h, cudaMemcpyAsync(recs, h->d_precs, sizeof(vdl2_avlc_t) * (size_t) nf, cudaMemcpyDeviceToHost, h->stream));
+		CK(h, cudaStreamSynchronize(h->stream));
+	}
+	{
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, h->pev0, h->pev1) == cudaSuccess)
+			h->last_pack_ms = ms;
+	}
+	h->st.frames_out += nf;
+	*n_frames = (int)nf;
+	*n_bytes = nb;
+	return 0;
+}
+
+/* device time of the ranking + packing + field kernels of the last vdl2_drain_frames_packed() (CUDA events) */
+extern "C" float vdl2_last_pack_ms(const vdl2gpu_t * h)
+{
+	return h ? h->last_pack_ms : 0.f;
 }
 
 /* ---- frame fields (row f4) ---- */

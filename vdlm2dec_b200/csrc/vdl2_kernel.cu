@@ -474,7 +474,7 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
  *     C[32 rows x 8] = A[32 rows x 64 window bytes] * B[64 x 8]      4 x mma.sync.m16n8k32 (u8 or s8 data, s8 weights, int32 sums)
  * instead of 72 IDP.4A + 24 PRMT + 24 LOP3 per row: the raw I,Q bytes ARE the A operand (no conversion, not even a sign flip:
  * unsigned bytes are undone exactly by the accumulator's start value), re and im get their own weight columns (digits 2,1,0 of
- * the 2^-22-quantised oscillator value), and the accumulator starts at the bits of 1.5 * 2^23 so that it leaves the tensor
+ * the oscillator value quantised to 1/8355711), and the accumulator starts at the bits of 1.5 * 2^23 so that it leaves the tensor
  * core as a float.  Same exact int32 sums as the IDP.4A mixer, so parity is untouched.
  *   - HBM -> shared memory: NON-overlapping TMA boxes of 32 rows x 64 bytes (64B swizzle) in a ring; a dump's window is the four
  *     16-byte chunks j0..j0+3 wherever they lie in the ring (at most two boxes), addressed chunk by chunk through ldmatrix.x4
@@ -485,13 +485,15 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
  *     shifts (first/last sample of the dump from the schedule word).
  *   - epilogue: lane (g, t) holds columns 2t, 2t+1 of rows g, g+8 (+16 for the second m16 tile).  t even: digits 2 and 1,
  *     t odd: digit 0 (and a duplicate column times zero); one shuffle with lane^1 completes the value, even lanes keep the
- *     first m16 tile and odd lanes the second; t < 2 is the real part, t >= 2 the imaginary part.
+ *     first m16 tile and odd lanes the second; t < 2 is the real part, t >= 2 the imaginary part, so a second shuffle with
+ *     lane^2 leaves every lane with (re, im) of ONE row.  Four dumps later the lane stores one full 32-byte sector of the
+ *     time-ordered scratch straight from registers (no transpose tile: its 2.3 KB pay for a fourth ring stage).
  */
 #define MM_NST VDL2_MM_NST
 #define MM_STAGE 2048		/* 32 rows x 64 bytes */
-#define MM_TPITCH 9		/* floats per row of one plane of the transpose tile */
-#define MM_TPLANE 296		/* floats between the real and the imaginary plane: 32 * 9 + 8 keeps the four lane groups on distinct banks */
-#define MM_TILE_BYTES (2 * MM_TPLANE * 4)
+#ifndef MM_UNROLL
+#define MM_UNROLL 2		/* dumps per store group: 2 = half a 32-byte sector per lane and store (A/B on B200: 1 % faster than 4, smaller loop) */
+#endif
 
 template < int FMT > __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t(&a)[4], uint32_t b0, uint32_t b1)
 {
@@ -537,8 +539,8 @@ __device__ __forceinline__ bool elect_one()
 #define VDL2_PINF(v) asm volatile ("" : "+f"(v))
 
 template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensorMap * tmap, const Vdl2KParams & kp, unsigned char *stage0,
-								unsigned long long *bars, float *tile, const uint4 * bt, uint32_t & phases, int row0,
-								int stream, const int4 * dtab, float2 * sd, unsigned long long l2pol)
+								unsigned long long *bars, const uint4 * bt, uint32_t & phases, int row0, int stream,
+								const int4 * dtab, float2 * sd, unsigned long long l2pol, unsigned long long l2keep)
 {
 	const int lane = threadIdx.x;
 	const unsigned *sched = c_tab.sched_slots[kp.sched_slot];
@@ -553,8 +555,10 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	float scx = (t & 1) ? 1.f : 65536.f, scy = (t & 1) ? 0.f : 256.f;
 	float nscx = -12582912.f * scx, nscy = -12582912.f * scy;	/* exact: powers of two */
 	int t32 = 32 * t;
-	uint32_t tw = smem_u32(tile + (t >> 1) * MM_TPLANE + (g + 16 * (t & 1)) * MM_TPITCH);	/* this lane's two rows: tw, tw + 8 rows */
-	uint32_t odd = (uint32_t) t & 1u;
+	uint32_t odd = (uint32_t) t & 1u, hi = (uint32_t) t >> 1;
+	/* after the two exchanges below this lane owns (re, im) of ONE row: g + 16 (t & 1) + 8 (t >> 1); four consecutive dumps of it
+	   are one 32-byte sector of the scratch */
+	float4 *dst = reinterpret_cast < float4 * >(sd + VDL2_HIST + (g + 16 * (t & 1) + 8 * (t >> 1)) * VDL2_DUMPS_PER_ROW);
 	VDL2_PIN(sw16);
 	VDL2_PIN(cwl16);
 	VDL2_PIN(rowoff);
@@ -564,81 +568,98 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	VDL2_PINF(nscx);
 	VDL2_PINF(nscy);
 	VDL2_PIN(t32);
-	VDL2_PIN(tw);
 	VDL2_PIN(odd);
+	VDL2_PIN(hi);
 	const float2 sc = make_float2(scx, scy), nsc = make_float2(nscx, nscy);
 	const int nbox = kp.nbox;
 	int st = 0, box = 0;
 	int4 dn = __ldg(dp);
 	mbar_wait(smem_u32(bars), phases & 1u);
 	phases ^= 1u;
+	static_assert(VDL2_DUMPS_PER_ROW % MM_UNROLL == 0 && (MM_NST & (MM_NST - 1)) == 0, "whole store groups per row; ring size a power of two");
 #pragma unroll 1
-	for (int dk = 0; dk < VDL2_DUMPS_PER_ROW; dk++) {
-		const int4 dc = dn;
-		const unsigned sk = sched[dk];
-		dp += 4;
-		dn = __ldg(dp);	/* the table carries one entry more than there are dumps */
-		const int st1 = (st + 1 == MM_NST) ? 0 : st + 1;
-		if (sk & VDL2_MM_W) {
-			mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
-			phases ^= 1u << st1;
-		}
-		const uint32_t base0 = rowoff + (uint32_t) st * MM_STAGE, base1 = rowoff + (uint32_t) st1 * MM_STAGE;
-		const uint32_t q0 = (sk & 0x30u) + cwl16, q1 = q0 + 32u;	/* 16 * (chunk of this lane's matrix counted from the box start) */
-		const uint32_t ad0 = (q0 >= 64u ? base1 : base0) + ((q0 ^ sw16) & 0x30u);
-		const uint32_t ad1 = (q1 >= 64u ? base1 : base0) + ((q1 ^ sw16) & 0x30u);
-		uint32_t a00[4], a01[4], a10[4], a11[4];	/* [m16 tile][k step] */
-		ldsm_x4(a00, ad0);
-		ldsm_x4(a10, ad0 + 1024u);
-		ldsm_x4(a01, ad1);
-		ldsm_x4(a11, ad1 + 1024u);
-		uint4 B;
-		asm volatile ("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];":"=r" (B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w):"r"(btl + ((sk & 0x3f00u) >> 2)));
-		const int o16 = (int)((sk >> 16) & 127u), te = t32 - (int)(sk >> 23);
-		B.x &= shl_clamp(0xffffffffu, (uint32_t) max(o16 - t32, 0));	/* samples 2t, 2t+1: keep those >= o */
-		B.z &= shr_clamp(0xffffffffu, (uint32_t) max(te + 288, 0));	/* samples 16+2t, 17+2t: keep those < e */
-		B.w &= shr_clamp(0xffffffffu, (uint32_t) max(te + 416, 0));	/* samples 24+2t, 25+2t */
-		int c0[4] = { dc.x, dc.y, dc.x, dc.y }, c1[4] = { dc.x, dc.y, dc.x, dc.y };
-		imma_16832 < FMT > (c0, a00, B.x, B.y);
-		imma_16832 < FMT > (c1, a10, B.x, B.y);
-		imma_16832 < FMT > (c0, a01, B.z, B.w);
-		imma_16832 < FMT > (c1, a11, B.z, B.w);
-		/* the accumulators are floats 12582912 + sum: remove the bias and weigh the digits in one exact FFMA2 each */
-		const float2 y0 = ffma2(make_float2(__int_as_float(c0[0]), __int_as_float(c0[1])), sc, nsc);
-		const float2 y1 = ffma2(make_float2(__int_as_float(c0[2]), __int_as_float(c0[3])), sc, nsc);
-		const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
-		const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
-		const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;	/* rows g, g + 8, g + 16, g + 24 */
-		const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
-		const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
-		const float sf = __int_as_float(dc.z), corr = __int_as_float(dc.w);
-		const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
-		const uint32_t twk = tw + 4u * ((uint32_t) dk & 7u);
-		asm volatile ("st.shared.f32 [%0], %1;"::"r" (twk), "f"(v0):"memory");
-		asm volatile ("st.shared.f32 [%0], %1;"::"r" (twk + 8 * MM_TPITCH * 4), "f"(v1):"memory");
-		__syncwarp();	/* every lane has consumed the window; the tile is complete for this dump */
-		if (sk & VDL2_MM_R) {
-			if (box + MM_NST < nbox && elect_one()) {
-				const uint32_t bar = smem_u32(bars + st);
-				mbar_expect_tx(bar, MM_STAGE);
-				tma_load_3d(smem_u32(stage0 + st * MM_STAGE), tmap, bar, (box + MM_NST) * 32, row0, stream, l2pol);
-			}
-			box++;
-			st = st1;
-		}
-		if ((dk & 7) == 7 || dk == VDL2_DUMPS_PER_ROW - 1) {
-			/* 8 (last group: 4) dumps x 32 rows -> scratch, 64 contiguous bytes per row */
-			const int k0 = dk & ~7, ng = dk - k0 + 1;
-			const int col = lane & 7, rsub = lane >> 3;
-			float2 *dst = sd + VDL2_HIST + k0 + col;
+	for (int dk0 = 0; dk0 < VDL2_DUMPS_PER_ROW; dk0 += MM_UNROLL) {
+		/* software pipeline over the MM_UNROLL dumps of a store group: first every dump's window and weights go to registers
+		   (waits, ldmatrix, B + masks), then the tensor-core products and epilogues run back to back while the loads of the
+		   later dumps are still in flight */
+		uint32_t a00[MM_UNROLL][4], a01[MM_UNROLL][4], a10[MM_UNROLL][4], a11[MM_UNROLL][4];	/* [dump][m16 tile, k step] */
+		uint4 B[MM_UNROLL];
+		int4 dc[MM_UNROLL];
+		int rst[MM_UNROLL], rbox[MM_UNROLL];	/* stage / box to refill after the dump (-1: none) */
 #pragma unroll
-			for (int it = 0; it < 8; it++) {
-				const int r = it * 4 + rsub;
-				if (col < ng)
-					__stcg(dst + r * VDL2_DUMPS_PER_ROW, make_float2(tile[r * MM_TPITCH + col], tile[MM_TPLANE + r * MM_TPITCH + col]));
+		for (int u = 0; u < MM_UNROLL; u++) {
+			dc[u] = dn;
+			const unsigned sk = sched[dk0 + u];
+			dp += 4;
+			dn = __ldg(dp);	/* the table carries one entry more than there are dumps */
+			const int st1 = (st + 1) & (MM_NST - 1);
+			if (sk & VDL2_MM_W) {
+				mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
+				phases ^= 1u << st1;
 			}
-			__syncwarp();
+			const uint32_t base0 = rowoff + (uint32_t) st * MM_STAGE, base1 = rowoff + (uint32_t) st1 * MM_STAGE;
+			const uint32_t q0 = (sk & 0x30u) + cwl16, q1 = q0 + 32u;	/* 16 * (chunk of this lane's matrix counted from the box start) */
+			const uint32_t ad0 = (q0 >= 64u ? base1 : base0) + ((q0 ^ sw16) & 0x30u);
+			const uint32_t ad1 = (q1 >= 64u ? base1 : base0) + ((q1 ^ sw16) & 0x30u);
+			ldsm_x4(a00[u], ad0);
+			ldsm_x4(a10[u], ad0 + 1024u);
+			ldsm_x4(a01[u], ad1);
+			ldsm_x4(a11[u], ad1 + 1024u);
+			asm volatile ("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];":"=r" (B[u].x), "=r"(B[u].y), "=r"(B[u].z), "=r"(B[u].w):"r"(btl + ((sk & 0x3f00u) >> 2)));
+			const int o16 = (int)((sk >> 16) & 127u), te = t32 - (int)(sk >> 23);
+			B[u].x &= shl_clamp(0xffffffffu, (uint32_t) max(o16 - t32, 0));	/* samples 2t, 2t+1: keep those >= o */
+			B[u].z &= shr_clamp(0xffffffffu, (uint32_t) max(te + 288, 0));	/* samples 16+2t, 17+2t: keep those < e */
+			B[u].w &= shr_clamp(0xffffffffu, (uint32_t) max(te + 416, 0));	/* samples 24+2t, 25+2t */
+			rst[u] = -1;
+			rbox[u] = 0;
+			if (sk & VDL2_MM_R) {	/* the next dump starts in the next box: this one can be refilled once its window is in registers */
+				if (box + MM_NST < nbox) {
+					rst[u] = st;
+					rbox[u] = box + MM_NST;
+				}
+				box++;
+				st = st1;
+			}
 		}
+		float2 out[MM_UNROLL];
+#pragma unroll
+		for (int u = 0; u < MM_UNROLL; u++) {
+			int c0[4] = { dc[u].x, dc[u].y, dc[u].x, dc[u].y }, c1[4] = { dc[u].x, dc[u].y, dc[u].x, dc[u].y };
+			imma_16832 < FMT > (c0, a00[u], B[u].x, B[u].y);
+			imma_16832 < FMT > (c1, a10[u], B[u].x, B[u].y);
+			imma_16832 < FMT > (c0, a01[u], B[u].z, B[u].w);
+			imma_16832 < FMT > (c1, a11[u], B[u].z, B[u].w);
+			if (rst[u] >= 0) {	/* the products above consumed the window: ldmatrix has completed for the whole warp */
+				__syncwarp();
+				if (elect_one()) {
+					const uint32_t bar = smem_u32(bars + rst[u]);
+					mbar_expect_tx(bar, MM_STAGE);
+					tma_load_3d(smem_u32(stage0 + rst[u] * MM_STAGE), tmap, bar, rbox[u] * 32, row0, stream, l2pol);
+				}
+			}
+			/* the accumulators are floats 12582912 + sum: remove the bias and weigh the digits in one exact FFMA2 each */
+			const float2 y0 = ffma2(make_float2(__int_as_float(c0[0]), __int_as_float(c0[1])), sc, nsc);
+			const float2 y1 = ffma2(make_float2(__int_as_float(c0[2]), __int_as_float(c0[3])), sc, nsc);
+			const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
+			const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
+			const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;	/* rows g, g + 8, g + 16, g + 24 */
+			/* lane ^ 1 holds the other digits: even lanes complete rows g, g + 8, odd lanes rows g + 16, g + 24 */
+			const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
+			const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
+			const float sf = __int_as_float(dc[u].z), corr = __int_as_float(dc[u].w);
+			const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
+			/* lane ^ 2 holds the other component of the same two rows: t < 2 keeps the first row, t >= 2 the second */
+			const float rx = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 2);
+			out[u] = make_float2(hi ? rx : v0, hi ? v1 : rx);
+		}
+		/* MM_UNROLL dumps of this lane's row, contiguous in the time-ordered scratch; evict-last: it is read back from L2 in phase 2 */
+		asm volatile ("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"::"l" (dst), "f"(out[0].x), "f"(out[0].y), "f"(out[1].x), "f"(out[1].y),
+			      "l"(l2keep):"memory");
+#if MM_UNROLL == 4
+		asm volatile ("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"::"l" (dst + 1), "f"(out[2].x), "f"(out[2].y), "f"(out[3].x), "f"(out[3].y),
+			      "l"(l2keep):"memory");
+#endif
+		dst += MM_UNROLL / 2;
 	}
 }
 
@@ -657,7 +678,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	unsigned char *stage0 = smem;
 	/* stages (+ the transpose tile of the integer mixer) | mbarriers | header soft bits | oscillator table */
 	/* DP: 0 generic fp32 mixer, 1 IDP.4A mixer, 2 int8 tensor-core mixer */
-	constexpr int STAGES_BYTES = DP == 2 ? MM_NST * MM_STAGE + MM_TILE_BYTES : (DP ? D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 : NSTAGE * STAGE_BYTES);
+	constexpr int STAGES_BYTES = DP == 2 ? MM_NST * MM_STAGE : (DP ? D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 : NSTAGE * STAGE_BYTES);
 	constexpr int NBAR = DP == 2 ? MM_NST : (DP ? D8_NST : NSTAGE);
 	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + STAGES_BYTES);
 	float *hv = reinterpret_cast < float *>(smem + STAGES_BYTES + 64);
@@ -728,6 +749,12 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	const int nco = kp.nco_pairs;
 	unsigned long long l2pol;	/* the input is read exactly once: evict-first keeps the per-warp scratch L2 resident */
 	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
+	unsigned long long l2keep;	/* the per-warp scratch: written in phase 1, read back in phase 2, should never reach DRAM */
+#ifdef VDL2_MM_NOKEEP	/* A/B */
+	asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;":"=l" (l2keep));
+#else
+	asm volatile ("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;":"=l" (l2keep));
+#endif
 	const uint32_t l7 = (uint32_t) (lane & 7);
 	float2 *sdrow = sd + VDL2_HIST + VDL2_DUMPS_PER_ROW * lane;
 
@@ -759,8 +786,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 			for (int i = lane; i < VDL2_MM_BT_ENTRIES; i += 32)
 				btsm[i] = __ldg(kp.w8 + (size_t) ch * VDL2_MM_BT_ENTRIES + i);
 			__syncwarp();
-			mix_rows_mma < FMT > (&tmap, kp, stage0, bars, reinterpret_cast < float *>(smem + MM_NST * MM_STAGE), btsm, phases, row0, stream,
-					      reinterpret_cast < const int4 * >(kp.dcorr) + (size_t) ch * VDL2_MM_DT_ENTRIES, sd, l2pol);
+			mix_rows_mma < FMT > (&tmap, kp, stage0, bars, btsm, phases, row0, stream,
+					      reinterpret_cast < const int4 * >(kp.dcorr) + (size_t) ch * VDL2_MM_DT_ENTRIES, sd, l2pol, l2keep);
 		} else if (DP) {
 			/* ---- phase 1, integer mixer: dump-aligned boxes, see mix_rows_dp4a ---- */
 			if (lane == 0) {
@@ -1009,7 +1036,7 @@ __global__ void vdl2_nsmid_kernel(unsigned *out)
 extern "C" int vdl2_kernel_smem_bytes(int nco_entries, int dp4a)
 {
 	if (dp4a == 2)
-		return MM_NST * MM_STAGE + MM_TILE_BYTES + 64 + 32 * 4 + VDL2_MM_BT_ENTRIES * 16;
+		return MM_NST * MM_STAGE + 64 + 32 * 4 + VDL2_MM_BT_ENTRIES * 16;
 	if (dp4a)
 		return D8_NST * D8_STAGE + 32 * D8_TPITCH * 8 + 64 + 32 * 4 + VDL2_W8_ENTRIES * 16;
 	return VDL2_NSTAGE * STAGE_BYTES + 64 + 32 * 4 + nco_entries * 16;

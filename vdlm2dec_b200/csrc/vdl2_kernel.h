@@ -16,7 +16,7 @@
 #endif
 
 #ifndef VDL2_MM_NST
-#define VDL2_MM_NST 3		/* 64-byte column boxes (32 rows x 64 B) in the ring per warp, tensor-core mixer */
+#define VDL2_MM_NST 4		/* 64-byte column boxes (32 rows x 64 B) in the ring per warp, tensor-core mixer */
 #endif
 
 #ifdef __cplusplus

@@ -391,7 +391,7 @@ vdl2_link_kernel(const Vdl2BlockRec * __restrict__ blocks, int nblocks, Vdl2Fram
 			fr->chn = blk->chn;
 			fr->Fr = blk->Fr;
 			fr->ppm = blk->ppm;
-			fr->pad = 0;
+			fr->pad = (int32_t) (blk->end_dump - blk->sync_dump);	/* burst duration in dumps: completion order for the packed drain */
 			fr->sync_dump = blk->sync_dump;
 		}
 		for (int i = lane; i < l; i += 32)

@@ -8,7 +8,7 @@
 struct Vdl2FrameRec {
 	int32_t block, len, chn, Fr;
 	float ppm;
-	int32_t pad;
+	int32_t pad;		/* end_dump - sync_dump of the block (vdl2_frame_t.pad) */
 	int64_t sync_dump;
 	uint8_t hdata[2016];
 };
@@ -25,6 +25,10 @@ int vdl2_link_launch(const Vdl2BlockRec * d_blocks, int nblocks, Vdl2FrameRec * 
 		     Vdl2BlkStat * d_stats, uint8_t * d_rows_after, void *stream);
 /* vdl2_avlc.cu (row f4): one 48-byte field record per frame */
 int vdl2_avlc_launch(const Vdl2FrameRec * d_frames, int nframes, void *d_recs, void *stream);
+/* frames (unordered, count on the device) -> completion-order rank, 16-byte aligned offsets, 32-byte headers + packed bytes,
+   field records in the same order; d_totals[0] = frames, [1] = bytes.  expect = host-side upper bound of the frame count */
+int vdl2_frames_pack_launch(const Vdl2FrameRec * d_frames, const unsigned *d_nframes, unsigned cap, int *d_rank, unsigned *d_offs,
+			    unsigned *d_totals, void *d_hdrs, uint8_t * d_bytes, unsigned bytes_cap, void *d_recs, int expect, void *stream);
 #ifdef __cplusplus
 }
 #endif

@@ -10,11 +10,11 @@
  *          window = the four 16-byte chunks j0 .. j0+3 holding the dump (j0 = first sample / 8)
  *     B  = 64 x 8 signed bytes: columns 0..2 = digits 2,1,0 of the real-part weights (wr for I bytes, -wi for Q bytes),
  *          columns 4..6 = digits of the imaginary-part weights (wi for I, wr for Q), columns 3 and 7 duplicates
- *          that are multiplied by zero afterwards; weights = round(w * 2^22) in balanced base-256 digits,
+ *          that are multiplied by zero afterwards; weights = round(w * 8355711) in balanced base-256 digits,
  *          zero outside the dump (the kernel masks the per-phase table with the dump's first/last sample)
  *     C0 = 0x4B400000 - 128 sum(B column over the dump)  (cu8: undoes the +128 of unsigned bytes exactly, in integers;
  *          0x4B400000 = bits of 1.5 * 2^23, so the int32 accumulator IS the float 12582912 + sum when it comes out)
- * The int32 sums are exact; the three digits are combined in fp32, scaled by 2^-22 / nf and corrected by
+ * The int32 sums are exact; the three digits are combined in fp32, scaled by 1 / (8355711 nf) and corrected by
  * delta * sum(w) for the 0.63 LSB between 128 and the reference's 127.37f (linear, evaluated in double here).
  */
 #ifndef VDL2_MMA_TABLES_H
@@ -25,6 +25,10 @@
 #include <vector>
 
 #define VDL2_MM_MAGIC 0x4B400000	/* float bits of 12582912 = 1.5 * 2^23 */
+/* oscillator weights are quantised to 1 / 8355711: the largest scale whose range [-1, 1] still fits three balanced base-256
+   digits (127 * 65536 + 127 * 256 + 127); quantisation error <= 6.0e-8, the size of one rounding of the reference's own
+   float products (the IDP.4A mixer of round 1 uses 2^-22: 1.2e-7) */
+#define VDL2_MM_WSCALE 8355711.0
 #define VDL2_MM_W 0x1u			/* sched bit: the dump's last chunk lies in a box not waited for yet */
 #define VDL2_MM_R 0x2u			/* sched bit: the current box is finished after this dump */
 
@@ -108,14 +112,14 @@ static inline void vdl2_mma_digits(int W, int dg[3])
 
 /* One channel.  bt[(p * 6 + c) * 4 + t] = the four B-fragment registers of lane (column c, t = lane & 3) for window
    phase p: {samples 2t,2t+1 | 8+2t,.. | 16+2t,.. | 24+2t,..}, each register = (w_I, w_Q) of two samples.
-   dt[k * 4 + t] = {C0 of column 2t, C0 of column 2t+1, bits of 2^-22/nf, bits of the offset correction (re for t < 2, im else)};
+   dt[k * 4 + t] = {C0 of column 2t, C0 of column 2t+1, bits of 1/(8355711 nf), bits of the offset correction (re for t < 2, im else)};
    dt has ndumps + 1 groups (the kernel prefetches one dump ahead), the last one a copy of the first. */
 static inline void vdl2_mma_build_chan(const float *wr, const float *wi, int nco_n, int row_samples, int sdrclk, int ndumps, bool cu8,
 				       Vdl2MmaU4 * bt, Vdl2MmaI4 * dt)
 {
 	std::vector < int >dr(3 * nco_n), di(3 * nco_n), dni(3 * nco_n);
 	for (int n = 0; n < nco_n; n++) {
-		const int qr = (int)lrint((double)wr[n] * 4194304.0), qi = (int)lrint((double)wi[n] * 4194304.0);
+		const int qr = (int)lrint((double)wr[n] * VDL2_MM_WSCALE), qi = (int)lrint((double)wi[n] * VDL2_MM_WSCALE);
 		vdl2_mma_digits(qr, &dr[3 * n]);
 		vdl2_mma_digits(qi, &di[3 * n]);
 		vdl2_mma_digits(-qi, &dni[3 * n]);
@@ -158,7 +162,7 @@ static inline void vdl2_mma_build_chan(const float *wr, const float *wi, int nco
 			swi += (double)wi[n];
 		}
 		const double s = 1.0 / (double)len[k];
-		const float sf = (float)(s / 4194304.0);
+		const float sf = (float)(s / VDL2_MM_WSCALE);
 		const float cre = (float)(delta * (swr - swi) * s), cim = (float)(delta * (swr + swi) * s);
 		for (int t = 0; t < 4; t++) {
 			Vdl2MmaI4 v;
