@@ -257,3 +257,29 @@ def out_text(hdata: bytes, chn: int = 0, Fr: int = 136_975_000, ppm: float = 0.0
     src = (C.c_uint8 * len(hdata)).from_buffer_copy(bytes(hdata))
     n = _avlc_lib("ref").orc_out_text(src, len(hdata), chn, Fr, C.c_float(ppm), C.c_double(t), buf, len(buf))
     return buf.raw[:n].decode("latin-1")
+
+
+def out_time(kind: str, data: np.ndarray, off: np.ndarray, length: np.ndarray, reps: int) -> float:
+    """Seconds for `reps` passes over packed frames through the reference's out() in JSON mode (kind "ref", one core), or through
+    the port's field walk (kind "port")."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    if kind == "ref":
+        lib = _avlc_lib("ref")
+        lib.orc_out_time.restype = C.c_double
+        lib.orc_out_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        return float(lib.orc_out_time(data.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), length.ctypes.data_as(C.c_void_p),
+                                      len(off), reps))
+    import time
+    lib = _avlc_lib("port")
+    rec = np.zeros(1, AVLC_DT)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for o, l in zip(off.tolist(), length.tolist()):
+            lib.orc_avlc_extract(data[o:o + l + 64].ctypes.data_as(C.c_void_p), l, rec.ctypes.data_as(C.c_void_p))
+    return time.perf_counter() - t0
+
+
+def out_available(kind: str) -> bool:
+    return os.path.exists(os.path.join(HERE, "libvdl2avlcport.so") if kind == "port" else os.path.join(HERE, "_ref", "libvdl2outref.so"))

@@ -69,3 +69,19 @@ static int run_out(const uint8_t * hdata, int l, int chn, int Fr, float ppm, dou
 	free(mem);
 	return (int)len;
 }
+
+/* seconds for `reps` passes of the reference's out() (JSON mode, -J -G -E) over n frames given as packed bytes:
+   frame i = bytes[off[i] .. off[i] + len[i]).  The CPU side of the row-f4 measurement (bench.py `avlc.cpu_baseline`):
+   it includes the reference's formatting, which the device record deliberately leaves to the host -- said so in the bench. */
+#include <time.h>
+double orc_out_time(const uint8_t * bytes, const uint32_t * off, const int32_t * len, int n, int reps)
+{
+	static char buf[60000];
+	struct timespec a, b;
+	clock_gettime(CLOCK_MONOTONIC, &a);
+	for (int r = 0; r < reps; r++)
+		for (int i = 0; i < n; i++)
+			orc_out_json(bytes + off[i], len[i], 0, 136975000, 0.0f, 0.0, buf, (int)sizeof buf);
+	clock_gettime(CLOCK_MONOTONIC, &b);
+	return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}

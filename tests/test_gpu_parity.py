@@ -95,12 +95,18 @@ def test_parity_three_mixers_for_8bit_input(fmt):
     ("cs16", 10_000_000, 2500, [-2_450_000, 1_175_000, 3_300_000, -50_000]),   # BASELINE config 5 shape (extension)
     ("f32real", 6_000_000, 1500, [1_250_000, 1_500_000 - 125_000, 2_100_000]),  # Airspy 6 Msps real (air.c:37-38)
     ("f32real", 5_000_000, 1250, [1_000_000, 1_250_000 + 75_000]),              # Airspy 5 Msps real (air.c:134-138)
+    # BASELINE config 5 "FIR-tap length sweep 64 -> 512": the reference's channel filter is the boxcar over one dump, fs / 84000
+    # samples long (d8psk.c:374-381), so the sweep that HAS an oracle is a rate sweep fs = 84 kHz x L, L = 75 / 125 / 250 / 500
+    ("cs16", 6_300_000, 1575, [-1_450_000, 2_075_000]),
+    ("cs16", 10_500_000, 2625, [-2_450_000, 3_300_000]),
+    ("cs16", 21_000_000, 5250, [-7_450_000, 9_300_000]),
+    ("cs16", 42_000_000, 10500, [-17_450_000, 12_300_000]),
 ])
 def test_parity_other_rates_and_formats(fmt, fs, sdrclk, fos):
     """cs16 and the Airspy real-sample mode at their own rates: the row is still 1 ms (fs/1000 samples,
     84 dumps), only the dump schedule, the NCO period (fs/25 kHz) and the chunk decoding change."""
     nch = len(fos) if fos else 4
-    n = fs // 1000 * 450
+    n = fs // 1000 * (450 if fs <= 10_000_000 else 160)
     specs, iq = make_channels(nch, n, seed=13, fs=fs, fmt=fmt, fos=fos, period=int(0.03 * fs))
     g = Vdl2Gpu([(c, 136_975_000, specs[c].Fo) for c in range(nch)], fs=fs, sdrclk=sdrclk, fmt=fmt, taps=SCREEN_TAPS,
                 max_samples=n)

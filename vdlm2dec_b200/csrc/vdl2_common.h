@@ -15,7 +15,7 @@
 #define VDL2_TILE_DUMPS (VDL2_DUMPS_PER_ROW * VDL2_ROWS_PER_TILE)	/* 2688 */
 #define VDL2_HIST 16		/* dumps of history in front of a tile (MBUFLEN-1) */
 #define VDL2_PHHIST 64		/* idle-mode phases of history ((NBPH-1)*D8DWN) */
-#define VDL2_MAX_CHUNKS 2560	/* 16-byte chunks per row: 40000 B (cs16 @ 10 Msps) / 16 */
+#define VDL2_MAX_CHUNKS 21000	/* 16-byte chunks per row: 336000 B (cf32 @ 42 Msps, the longest window of the config-5 sweep: 500 samples per dump) / 16 */
 #define VDL2_SCHED_SLOTS 16	/* distinct (fs, SDRCLK, format) combinations alive in one process */
 #define VDL2_W8_PHASES 104	/* integer mixer: oscillator entries by NCO phase, 80 + 24 so that a dump never wraps */
 #define VDL2_W8_ENTRIES 120	/* ... plus 16 "first sample only" entries closing the 23-sample dumps of a row */

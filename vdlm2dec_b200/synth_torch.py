@@ -56,11 +56,13 @@ class BurstLibrary:
 
 
 def make_device_workload(nch: int, nsamples: int, seed: int, device, fs: int = 2_000_000, fos=None,
-                         noise_sigma: float = 8.0, gap=(0.15, 0.6), group: int = 16, lib: BurstLibrary | None = None):
-    """-> (uint8 tensor [nch, 2*nsamples], list of Fo per channel, number of bursts placed)."""
+                         noise_sigma: float = 8.0, gap=(0.15, 0.6), group: int = 16, lib: BurstLibrary | None = None,
+                         fmt: str = "cu8", first_burst=None):
+    """-> (uint8 tensor [nch, 2*nsamples] for cu8, int16 for cs16 (the same signal x 64), list of Fo per channel, number of bursts placed).
+    first_burst: latest start of a channel's first burst in seconds (default 0.25)."""
     fos = fos or [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
     lib = lib or BurstLibrary(seed, device, fs)
-    out = torch.empty((nch, 2 * nsamples), dtype=torch.uint8, device=device)
+    out = torch.empty((nch, 2 * nsamples), dtype=torch.uint8 if fmt == "cu8" else torch.int16, device=device)
     rng = np.random.default_rng(seed + 1)
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + 2)
@@ -71,7 +73,7 @@ def make_device_workload(nch: int, nsamples: int, seed: int, device, fs: int = 2
         x = torch.randn((g, nsamples), dtype=torch.complex64, device=device, generator=gen) * (noise_sigma * math.sqrt(2.0))
         for i in range(g):
             fo = ch_fo[c0 + i]
-            t = int(rng.uniform(2000, 0.25 * fs))
+            t = int(rng.uniform(fs // 1000, (first_burst or 0.25) * fs))
             while True:
                 b, w = lib.items[int(rng.integers(0, len(lib.items)))]
                 L = w.numel()
@@ -87,7 +89,10 @@ def make_device_workload(nch: int, nsamples: int, seed: int, device, fs: int = 2
                 nb_total += 1
                 t += L + int(rng.uniform(*gap) * fs)
         iq = torch.view_as_real(x)  # [g, ns, 2]
-        q = (iq + 127.37).round_().clamp_(0, 255).to(torch.uint8)
+        if fmt == "cu8":
+            q = (iq + 127.37).round_().clamp_(0, 255).to(torch.uint8)
+        else:
+            q = (iq * 64.0).round_().clamp_(-32768, 32767).to(torch.int16)
         out[c0:c0 + g] = q.reshape(g, 2 * nsamples)
         del x, iq, q
     return out, ch_fo, nb_total
