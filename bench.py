@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5],
+                    help="BASELINE.json config: 3 (default; config 4 = the same per GPU at N=8) 1024 x 2 Msps cu8, one channel per stream; "
+                         "2 = 8 channels from ONE 2 Msps cu8 stream (the rtl.c shape); 5 = 8 channels from one cs16 stream at the "
+                         "Airspy-class rate 10.5 Msps, plus the window-length sweep fs = 84 kHz x {75, 125, 250, 500}")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle self-check of the timed workload")
     ap.add_argument("--check-channels", type=int, default=8)
     return ap.parse_args()
@@ -213,7 +217,7 @@ def bind_near_gpu(local_rank):
         return None
 
 
-def self_check(x, chans, fos, ns, cps, device, nchk):
+def self_check(x, chans, fos, ns, cps, device, nchk, fs=FS, sdrclk=500, fmt="cu8"):
     """`nchk` channels of the timed tensor (spread over the channel range) through a fresh handle, against the CPU checker
     (oracle/_ref = the reference's d8psk.c when present, else the port) fed the same bytes: completed blocks bit exact."""
     import numpy as np
@@ -232,17 +236,17 @@ def self_check(x, chans, fos, ns, cps, device, nchk):
     pick = sorted({int(i * (nstreams - 1) / max(1, nchk - 1)) for i in range(nchk)})
     sub = x[pick].contiguous()
     sel = [c for s_ in pick for c in range(s_ * cps, (s_ + 1) * cps)]
-    g = Vdl2Gpu([chans[c] for c in sel], ch_per_stream=cps, device=device, max_samples=ns)
-    g.process_device(sub.data_ptr(), ns, sub.stride(0))
+    g = Vdl2Gpu([chans[c] for c in sel], fs=fs, sdrclk=sdrclk, fmt=fmt, ch_per_stream=cps, device=device, max_samples=ns)
+    g.process_device(sub.data_ptr(), ns, sub.stride(0) * sub.element_size())
     g.sync()
     blocks = g.drain_blocks()
     host = sub.cpu().numpy()
     nblk, bad = 0, []
     for i, c in enumerate(sel):
         chn, Fr, Fo = chans[c]
-        o = pyoracle.Oracle(kind, chn=chn, Fr=Fr, Fo=Fo, taps=pyoracle.TAP_BLOCKS).feed(host[i // cps])
+        o = pyoracle.Oracle(kind, chn=chn, Fr=Fr, Fo=Fo, fs=fs, sdrclk=sdrclk, taps=pyoracle.TAP_BLOCKS).feed(host[i // cps], fmt)
         want = o.blocks
-        want = want[want["end_dump"] < ns // 2000 * 84]
+        want = want[want["end_dump"] < ns // (fs // 1000) * 84]
         got = blocks[blocks["chn"] == chn]
         same = len(want) == len(got) and all(
             a["sync_dump"] == b["sync_dump"] and a["end_dump"] == b["end_dump"] and a["nbrow"] == b["nbrow"] and a["nlbyte"] == b["nlbyte"]
@@ -253,6 +257,41 @@ def self_check(x, chans, fos, ns, cps, device, nchk):
     return {"ok": not bad and nblk > 0, "channels": len(sel), "blocks": int(nblk), "mismatching_channels": bad,
             "checker": "reference d8psk.c (oracle/_ref, -O2)" if kind == "ref" else "oracle port",
             "what": "completed blocks (trigger/end position, nbrow, nlbyte, data[8][255]) bit exact"}
+
+
+def config5_sweep(dev, local_rank, peak, steps):
+    """BASELINE config 5's "FIR-tap length sweep 64 -> 512".  The reference has no taps: its channel filter is the boxcar over one
+    dump, fs / 84000 samples long (d8psk.c:374-381), so the sweep that has an oracle is the rate sweep fs = 84 kHz x L with fs a
+    multiple of 25 kHz: L = 75, 125, 250, 500 (6.3 / 10.5 / 21 / 42 Msps), 8 channels from one cs16 stream, every point checked
+    against the CPU checker on the timed tensor."""
+    import numpy as np
+    import torch
+    from vdlm2dec_b200.api import Vdl2Gpu
+    from vdlm2dec_b200.synth_torch import make_device_workload
+    out = []
+    for L in (75, 125, 250, 500):
+        fs = 84_000 * L
+        ns = fs // 1000 * (1600 if L <= 125 else (800 if L == 250 else 400))
+        span = (fs // 2 - 100_000) // 25_000 * 25_000
+        raster = [int(f) // 25_000 * 25_000 for f in np.linspace(-span, span, 8)]
+        x, fos, nb = make_device_workload(1, ns, seed=500 + L, device=dev, fs=fs, fmt="cs16", fos=raster, ch_per_stream=8,
+                                          first_burst=0.01, gap=(0.02, 0.05))
+        chans = [(c, 136_000_000 + fos[c] % 1_000_000, fos[c]) for c in range(8)]
+        g = Vdl2Gpu(chans, fs=fs, sdrclk=fs // 4000, fmt="cs16", ch_per_stream=8, device=local_rank, max_samples=ns, max_blocks=(steps + 4) * max(nb, 64) + 4096)
+        ms = []
+        for _ in range(steps + 1):
+            g.process_device(x.data_ptr(), ns, x.stride(0) * x.element_size())
+            g.sync()
+            ms.append(g.stats()["last_kernel_ms"])
+            g.drain_blocks()
+        t = float(np.median(ms[1:]))
+        par = self_check(x, chans, fos, ns, 8, local_rank, 1, fs=fs, sdrclk=fs // 4000, fmt="cs16")
+        out.append({"window_samples": L, "fs": fs, "samples": ns, "bursts": nb, "kernel_ms": t, "msamples_per_s": 8 * ns / t / 1e3,
+                    "stream_gbs": ns * 4 / t / 1e6, "frac_of_hbm_peak": ns * 4 / t / 1e6 / peak, "parity_ok": par["ok"], "parity_blocks": par["blocks"]})
+        g.close()
+        del x
+        torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -275,26 +314,35 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    nch, ns = args.channels, args.samples // 2000 * 2000
+    fs, sdrclk, fmt, bps = FS, 500, "cu8", 2
+    if args.config == 2:      # the reference's own use: up to 8 frequencies from one 2 MHz stream (README.md:4, vdlm2.h:26)
+        args.channels, args.ch_per_stream = 8, 8
+    elif args.config == 5:    # Airspy-class rate, cs16 (extension; the reference's Airspy mode is float32 real at 5/6 Msps, air.c:123,134-138)
+        args.channels, args.ch_per_stream = 8, 8
+        fs, sdrclk, fmt, bps = 10_500_000, 2625, "cs16", 4
+        args.samples = min(args.samples * 4, 1 << 24)
+    nch, ns = args.channels, args.samples // (fs // 1000) * (fs // 1000)
     cps = args.ch_per_stream
     nstreams = nch // cps
     t_gen = time.time()
-    x, fos, nbursts = make_device_workload(nstreams, ns, seed=1000 + 17 * rank, device=dev)
-    if cps > 1:  # shared streams: channel c listens at its own Fo on stream c // cps
-        allfo = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
-        chans = [(c, 136_000_000 + allfo[c % cps], allfo[c % cps] if (c % cps) else fos[c // cps]) for c in range(nch)]
+    if fs == FS:
+        raster = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
     else:
-        chans = [(c + rank * nch, 136_975_000, fos[c]) for c in range(nch)]
+        span = (fs // 2 - 100_000) // 25_000 * 25_000
+        raster = [int(f) // 25_000 * 25_000 for f in np.linspace(-span, span, 8)]
+    x, fos, nbursts = make_device_workload(nstreams, ns, seed=1000 + 17 * rank, device=dev, fs=fs, fmt=fmt, fos=raster, ch_per_stream=cps,
+                                           amp=(12.0, 18.0) if (cps > 1 and fmt == "cu8") else (25.0, 70.0))
+    chans = [(c + rank * nch, 136_975_000 if cps == 1 else 136_000_000 + fos[c] % 1_000_000, fos[c]) for c in range(nch)]
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
     # OPT_OVERLAP: back-to-back launches may overlap on the device (programmatic dependent launch); the library then
     # records no per-launch events, the bench brackets with its own
-    g = Vdl2Gpu(chans, ch_per_stream=cps, device=local_rank, max_samples=ns, taps=OPT_OVERLAP,
-                max_blocks=(args.steps + 4) * max(nbursts, 64) * cps + 4096)
+    g = Vdl2Gpu(chans, fs=fs, sdrclk=sdrclk, fmt=fmt, ch_per_stream=cps, device=local_rank, max_samples=ns, taps=OPT_OVERLAP,
+                max_blocks=(args.steps + 4) * max(nbursts, 64) + 4096)
     stream = torch.cuda.ExternalStream(g.cuda_stream, device=dev)
 
     def step():
-        g.process_device(x.data_ptr(), ns, x.stride(0))
+        g.process_device(x.data_ptr(), ns, x.stride(0) * x.element_size())
 
     # ---- warm-up (also validates: every placed burst must come back as a block -- checked below on the FIRST step,
     #      which starts from a fresh state; later steps re-feed the buffer with carried state, so their seams add events)
@@ -348,7 +396,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- self-check of what was timed: channels of the timed tensor through a fresh handle vs the CPU oracle, blocks bit exact
     parity = None
     if rank == 0 and not args.no_check:
-        parity = self_check(x, chans, fos, ns, cps, local_rank, args.check_channels)
+        parity = self_check(x, chans, fos, ns, cps, local_rank, args.check_channels, fs=fs, sdrclk=sdrclk, fmt=fmt)
         if not parity["ok"]:
             raise SystemExit("bench.py: the timed workload does NOT decode like the oracle: " + json.dumps(parity))
     if blocks_first < nbursts - max(2, nbursts // 200):   # a burst cut by the end of the buffer may be missing
@@ -358,17 +406,17 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         old_affinity = bind_near_gpu(local_rank) if world > 1 else None
-        hx = torch.empty((nstreams, 2 * ns), dtype=torch.uint8, pin_memory=True)
+        hx = torch.empty((nstreams, 2 * ns), dtype=x.dtype, pin_memory=True)
         hx.copy_(x)
         torch.cuda.synchronize()
         nrep = max(2, min(args.steps, 4))
-        g.process_ptr(hx.data_ptr(), ns, hx.stride(0))
+        g.process_ptr(hx.data_ptr(), ns, hx.stride(0) * hx.element_size())
         g.drain_blocks()
         barrier()
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(nrep):
-            g.process_ptr(hx.data_ptr(), ns, hx.stride(0))  # returns after the kernel finished
+            g.process_ptr(hx.data_ptr(), ns, hx.stride(0) * hx.element_size())  # returns after the kernel finished
             d2h += g.drain_blocks().nbytes + 32
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -376,7 +424,7 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": nch * ns * nrep * world / float(tt.item()) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep,
+               "h2d_bytes_per_step": int(hx.numel() * hx.element_size()), "d2h_bytes_per_step": int(d2h // nrep), "steps": nrep,
                "host_numa_bound": old_affinity is not None}
         del hx
         if old_affinity is not None:
@@ -467,7 +515,7 @@ def run_ours(args, rank, local_rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = nstreams * ns * 2  # 2 B per cu8 IQ sample per stream; output bytes are negligible
+    alg_bytes = nstreams * ns * bps  # 2 B per cu8 (4 B per cs16) IQ sample per STREAM; output bytes are negligible
     kms_region = ms_total / args.steps  # rank 0, CUDA events on the launching stream over the timed region
     achieved = alg_bytes / (kms_region * 1e-3) / 1e9
     traffic = None
@@ -482,24 +530,30 @@ def run_ours(args, rank, local_rank, world):
                 "kernel": "vdl2_frontend_kernel", "kernel_ms": kms_region, "kernel_ms_isolated": kms, "algorithmic_bytes_per_launch": alg_bytes}
 
     cpu = None
-    if not args.no_cpu and world == 1:
-        nrows = 4
+    if not args.no_cpu and world == 1 and fmt == "cu8":
+        nrows = min(4, nstreams)
         sub = x[:nrows, : 2 * min(ns, 1 << 21)].cpu().numpy()
         v, cores, kind, desc = cpu_throughput(sub, fos[:nrows], args.cpu_seconds)
         cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": desc}
 
+    sweep = config5_sweep(dev, local_rank, peak, 3) if args.config == 5 else None
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{nch} channels/GPU x {ns} samples, 2 Msps cu8 IQ, {cps} ch/stream (BASELINE config 3; "
-                               f"config 4 = the same per GPU at N=8)", "channels_per_gpu": nch, "samples_per_channel": ns,
-                   "bytes_per_step_per_gpu": alg_bytes, "l2": "input per step (8 GiB at defaults) >> 126 MB L2; no flush needed",
+        "config": {"workload": f"{nch} channels/GPU x {ns} samples, {fs / 1e6:g} Msps {fmt} IQ, {cps} ch/stream (BASELINE config "
+                               + {3: "3; config 4 = the same per GPU at N=8)", 2: "2: 8 channels from one stream, the rtl.c shape)",
+                                  5: "5 at window length 125; see `sweep`)"}[args.config],
+                   "baseline_config": args.config, "channels_per_gpu": nch, "samples_per_channel": ns,
+                   "bytes_per_step_per_gpu": alg_bytes,
+                   "l2": "input per step (8 GiB at defaults) >> 126 MB L2; no flush needed" if alg_bytes > (1 << 29) else
+                         "input per step fits the 126 MB L2: the shared stream is read once from HBM and cps times from L2 by design "
+                         "(FP32/tensor issue bound, not HBM bound; the HBM fraction is reported for completeness)",
                    "bursts_per_step_per_gpu": nbursts, "blocks_decoded_per_step": blocks_timed // max(1, args.steps) if blocks_timed else blocks_seen,
                    "parallelism": f"channels sharded, {world} GPU(s), no collective", "gen_seconds": round(t_gen, 1),
                    "launch_mode": "back-to-back launches with programmatic dependent launch (tails overlap)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "parity_checked": parity, "blocks_first_step": blocks_first, "link": link,
+        "parity_checked": parity, "blocks_first_step": blocks_first, "link": link, "sweep": sweep,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -75,6 +75,8 @@ void orc_clear_taps(void *h);
 int64_t orc_ndump(void *h);
 const char *orc_kind(void);
 const float *orc_table(int which);
+/* oscillator table of an open handle (d8psk.c:353-357): up to max complex floats into out[2 * max]; returns the table length */
+int orc_nco(void *h, float *out, int max);
 double orc_time_cu8(int Fr, int Fo, unsigned fs, unsigned sdrclk, const uint8_t * iq, size_t n, int reps);
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ def load(kind: str):
     lib.orc_kind.restype = C.c_char_p
     lib.orc_table.restype = C.POINTER(C.c_float)
     lib.orc_table.argtypes = [C.c_int]
+    lib.orc_nco.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.orc_time_cu8.restype = C.c_double
     lib.orc_time_cu8.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t, C.c_int]
     _LIBS[kind] = lib
@@ -131,6 +132,13 @@ class Oracle:
             return np.zeros(0, dtype=dt)
         buf = (C.c_char * (n.value * np.dtype(dt).itemsize)).from_address(p)
         return np.frombuffer(buf, dtype=dt).copy()
+
+    @property
+    def nco(self) -> np.ndarray:
+        """The channel's oscillator table wf[] (d8psk.c:353-357) as complex64."""
+        out = np.zeros(2 * 4096, np.float32)
+        n = self.lib.orc_nco(self.h, out.ctypes.data_as(C.c_void_p), 4096)
+        return out[:2 * n].view(np.complex64).copy()
 
     @property
     def dumps(self):

@@ -373,6 +373,18 @@ const char *orc_kind(void)
 }
 
 /* the reference's own constant tables (d8psk.h), for the known-answer tests */
+/* the oscillator table of an open handle, exactly as d8psk.c:353-357 builds it (cexpf): n complex floats -> out[2n] */
+int orc_nco(void *h, float *out, int max)
+{
+	refctx *c = h;
+	int n = c->nwf < max ? c->nwf : max;
+	for (int i = 0; i < n; i++) {
+		out[2 * i] = crealf(c->wf[i]);
+		out[2 * i + 1] = cimagf(c->wf[i]);
+	}
+	return c->nwf;
+}
+
 const float *orc_table(int which)
 {
 	switch (which) {

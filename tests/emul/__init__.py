@@ -69,6 +69,16 @@ def mma_mix(rows: np.ndarray, Fo: int, cu8: bool = True, fs: int = 2_000_000, sd
     return (out[..., 0] + 1j * out[..., 1]).astype(np.complex64).reshape(-1), rc
 
 
+def nco_table(Fo: int, fs: int) -> np.ndarray:
+    """The product's oscillator table for (Fo, fs): vdl2_nco_table of vdl2_mma_tables.h, what vdl2_host.cu uploads."""
+    global _mma
+    if _mma is None:
+        _mma = C.CDLL(build_mma())
+    out = np.zeros(2 * (fs // 25000), np.float32)
+    _mma.emul_nco_table(int(Fo), C.c_uint(fs), out.ctypes.data_as(C.c_void_p))
+    return out.view(np.complex64)
+
+
 def build():
     build_avlc()
     build_mma()

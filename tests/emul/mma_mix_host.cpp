@@ -209,3 +209,16 @@ extern "C" int emul_mma_mix(const uint8_t * rows, int nrows, unsigned fs, unsign
 			E.errors++;
 	return E.errors;
 }
+
+/* the PRODUCT's oscillator table (vdl2_nco_table, the function vdl2_host.cu builds every mixer table from) */
+extern "C" int emul_nco_table(int Fo, unsigned fs, float *out)
+{
+	const int n = (int)(fs / 25000);
+	std::vector < float >wr(n), wi(n);
+	vdl2_nco_table(Fo, fs, n, wr.data(), wi.data());
+	for (int i = 0; i < n; i++) {
+		out[2 * i] = wr[i];
+		out[2 * i + 1] = wi[i];
+	}
+	return n;
+}

@@ -144,3 +144,28 @@ def test_golden_fixture_port():
     assert np.array_equal(o.syms["D"].view(np.uint32), g["sym_D"].view(np.uint32))
     assert np.array_equal(o.syms["gi"], g["sym_gi"])
     assert o.blocks.tobytes() == g["blocks"].tobytes()
+
+
+@pytest.mark.parametrize("fs", [2_000_000, 5_000_000, 6_000_000, 6_300_000, 10_000_000, 10_500_000, 21_000_000, 42_000_000])
+def test_nco_table_bit_identical_to_reference(fs):
+    """Row a4: the oscillator table every mixer table of the product is built from (vdl2_nco_table: cosf / sinf of the float
+    product -n * Fo', vdl2_mma_tables.h) against the reference's wf[n] = cexpf(-n * Fo' * I) (d8psk.c:353-357, compiled in place)
+    and against the port, bit for bit, for EVERY Fo of the 25 kHz raster inside the band at every supported rate."""
+    from tests import emul
+    kinds = ["port"] + (["ref"] if HAVE_REF else [])
+    step = 25_000 if fs <= 6_300_000 else 25_000 * 7   # the wide rates have thousands of raster points: every 7th (all residues mod 80 periods still appear)
+    n = 0
+    for Fo in range(-(fs // 2) + 50_000, fs // 2 - 25_000, step):
+        if Fo == 0:
+            continue
+        mine = emul.nco_table(Fo, fs)
+        assert len(mine) == fs // 25000
+        for kind in kinds:
+            o = Oracle(kind, Fo=Fo, fs=fs, sdrclk=fs // 4000, taps=0)
+            ref = o.nco
+            o.close()
+            assert ref.view(np.uint32).tolist() == mine.view(np.uint32).tolist(), f"{kind}: NCO table differs at fs {fs} Fo {Fo}"
+        n += 1
+    assert n >= 30
+    if not HAVE_REF:
+        pytest.skip("oracle/_ref not present: pinned against the port only")

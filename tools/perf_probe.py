@@ -25,7 +25,7 @@ import os
 g = Vdl2Gpu(chans, ch_per_stream=cps, max_samples=ns, taps=0x400 if os.environ.get('VDL2_OVERLAP') else 0)
 torch.cuda.synchronize()
 for r in range(reps):
-    g.process_device(x.data_ptr(), ns, x.stride(0))
+    g.process_device(x.data_ptr(), ns, x.stride(0) * x.element_size())
     g.sync()
     st = g.stats()
     ms = st["last_kernel_ms"] or 1e-9
@@ -38,7 +38,7 @@ if os.environ.get('VDL2_OVERLAP'):   # back-to-back launches, timed as a whole
     g.sync()
     e0.record(st)
     for _ in range(K):
-        g.process_device(x.data_ptr(), ns, x.stride(0))
+        g.process_device(x.data_ptr(), ns, x.stride(0) * x.element_size())
     e1.record(st)
     g.sync()
     ms = e0.elapsed_time(e1) / K

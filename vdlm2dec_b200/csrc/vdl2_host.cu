@@ -62,7 +62,8 @@ struct vdl2gpu {
 	unsigned *d_slotmask;
 	unsigned nsmid;
 	int *d_progress;
-	int tiles_done;		/* per channel, since create */
+	unsigned tiles_done;	/* per channel, since create (wraps; the kernel compares differences) */
+	bool last_was_launch;	/* the newest operation on the stream is a front-end launch (programmatic dependent launch is safe behind it) */
 	unsigned launch_seq;
 	bool overlap;		/* VDL2_OPT_OVERLAP: no per-launch events, consecutive launches may overlap */
 	uint8_t *d_curblk;
@@ -406,15 +407,11 @@ static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_p
 	/* NCO tables, d8psk.c:353-357 */
 	std::vector < float4 > wt((size_t) nch * h->nco_entries);
 	for (int c = 0; c < nch; c++) {
-		const float Fo = (float)((float)chans[c].Fo / (float)(cfg->fs) * 2.0 * M_PI);
+		/* cexpf(-n*Fo*I) = (cosf(a), sinf(a)) with the float product a = -n*Fo: vdl2_nco_table (vdl2_mma_tables.h) is the one
+		   implementation every mixer table is built from; tests/test_oracle.py::test_nco_table_bit_identical_to_reference pins
+		   it against the reference's cexpf table over the whole 25 kHz raster at every supported rate */
 		std::vector < float >wr(nco_n), wi(nco_n);
-		for (int n = 0; n < nco_n; n++) {
-			/* cexpf(-n*Fo*I) = (cosf(a), sinf(a)) with the float product a = -n*Fo; glibc's
-			   cexpf evaluates exactly this pair (checked bit for bit in tests/test_oracle.py) */
-			const float a = (float)(-n) * Fo;
-			wr[n] = cosf(a);
-			wi[n] = sinf(a);
-		}
+		vdl2_nco_table(chans[c].Fo, cfg->fs, nco_n, wr.data(), wi.data());
 		float4 *dst = wt.data() + (size_t) c * h->nco_entries;
 		if (cfg->format == VDL2_FMT_CF32) {
 			for (int n = 0; n < nco_n; n++)
@@ -736,7 +733,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	kp.ticket = h->d_ticket;
 	kp.ticket_sel = (int)(h->launch_seq % 3u);
 	kp.launch_seq = (int)h->launch_seq;
-	kp.tile_base = h->tiles_done;
+	kp.tile_base = (int)h->tiles_done;
 	kp.progress = h->d_progress;
 	kp.slotmask = h->d_slotmask;
 	kp.slots_per_sm = h->ctas_per_sm;
@@ -772,7 +769,7 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	const int grid = (int)std::min < long long >(items, h->grid);
 	if (!h->overlap)	/* an event between two kernels would serialise them */
 		CK(h, cudaEventRecord(h->ev0, h->stream));
-	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, h->dp4a, &tmap, &kp, grid, h->smem, h->stream);
+	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, h->dp4a, &tmap, &kp, grid, h->smem, h->stream, h->overlap && h->last_was_launch && base != (const void *)h->d_stage);
 	if (e != cudaSuccess)
 		return fail(h, "kernel launch failed: %s", cudaGetErrorString(e));
 	if (!h->overlap) {
@@ -786,7 +783,8 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 		h->mirror_seq++;
 	}
 	h->launch_seq++;
-	h->tiles_done += kp.ntiles;
+	h->tiles_done += (unsigned)kp.ntiles;
+	h->last_was_launch = !h->h_mirror;	/* a mirror copy behind the launch is an ordinary stream operation */
 	h->st.kernel_launches++;
 	h->st.grid = grid;
 	h->rows_done += nrows;
@@ -1104,7 +1102,7 @@ static int link_run(vdl2gpu * h, const Vdl2BlockRec * d_blocks, int nblocks, vdl
 	*n_frames = 0;
 	if (nblocks <= 0)
 		return 0;
-	CK(h, cudaMemsetAsync(h->d_nframes, 0, 4, h->stream));
+	CK(h, cudaMemsetAsync(h->d_nframes, 0, 8, h->stream));
 	CK(h, cudaEventRecord(h->lev0, h->stream));
 	cudaError_t e = (cudaError_t) vdl2_link_launch(d_blocks, nblocks, h->d_frames, h->d_nframes, (unsigned)std::min(max_frames, h->lcap_frames),
 						       h->d_lstats, want_rows ? h->d_lrows : NULL, h->stream);
@@ -1113,9 +1111,12 @@ static int link_run(vdl2gpu * h, const Vdl2BlockRec * d_blocks, int nblocks, vdl
 	CK(h, cudaEventRecord(h->lev1, h->stream));
 	h->lev_valid = true;
 	h->st.link_launches++;
-	unsigned nf = 0;
-	CK(h, cudaMemcpyAsync(&nf, h->d_nframes, 4, cudaMemcpyDeviceToHost, h->stream));
+	unsigned nfv[2] = { 0, 0 };
+	CK(h, cudaMemcpyAsync(nfv, h->d_nframes, 8, cudaMemcpyDeviceToHost, h->stream));
 	CK(h, cudaStreamSynchronize(h->stream));
+	const unsigned nf = nfv[0];
+	if (nfv[1])	/* more FCS-good candidates in one block than the kernel hands over: never silently */
+		return fail(h, "block pipeline: %u candidate frames beyond the per-block limit were not delivered", nfv[1]);
 	if ((int)nf > max_frames || (int)nf > h->lcap_frames)
 		return fail(h, "block pipeline: %u frames, room for %d", nf, std::min(max_frames, h->lcap_frames));
 	if (nf) {
@@ -1265,7 +1266,7 @@ extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, 
 		CK(h, cudaEventCreate(&h->pev1));
 	}
 	const unsigned cap = (unsigned)std::min(fcap, h->lcap_frames);
-	CK(h, cudaMemsetAsync(h->d_nframes, 0, 4, h->stream));
+	CK(h, cudaMemsetAsync(h->d_nframes, 0, 8, h->stream));
 	CK(h, cudaEventRecord(h->lev0, h->stream));
 	cudaError_t e = (cudaError_t) vdl2_link_launch(h->d_outq, (int)n, h->d_frames, h->d_nframes, cap, h->d_lstats, NULL, h->stream);
 	if (e != cudaSuccess)
@@ -1288,8 +1289,11 @@ extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, 
 			h->h_mirror[16 * i + 4] = 0;
 	h->st.blocks_out += n;
 	const unsigned nf = h->h_totals[0], nb = h->h_totals[1];
-	unsigned raw = 0;
-	CK(h, cudaMemcpy(&raw, h->d_nframes, 4, cudaMemcpyDeviceToHost));
+	unsigned rawv[2] = { 0, 0 };
+	CK(h, cudaMemcpy(rawv, h->d_nframes, 8, cudaMemcpyDeviceToHost));
+	const unsigned raw = rawv[0];
+	if (rawv[1])
+		return fail(h, "block pipeline: %u candidate frames beyond the per-block limit were not delivered", rawv[1]);
 	if (raw > cap || (int)nf > max_frames)
 		return fail(h, "vdl2_drain_frames_packed: %u frames, room for %d", raw, std::min(max_frames, (int)cap));
 	if (nb > max_bytes)

@@ -713,7 +713,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	   channel's chain).  Work counters rotate over three slots: this launch uses ticket[ticket_sel] and clears the one
 	   the NEXT launch will use (last used two launches ago).  Only then may the next launch start. */
 	if (lane == 0) {
-		while ((int)(*(volatile unsigned *)(kp.ticket + 3)) < kp.launch_seq - 1)
+		/* counters count since create and wrap after 2^32: compare differences, never values */
+		while ((int)((unsigned)kp.launch_seq - 1u - *(volatile unsigned *)(kp.ticket + 3)) > 0)
 			__nanosleep(500);
 		if (blockIdx.x == 0) {
 			kp.ticket[(kp.ticket_sel + 1) % 3] = 0u;
@@ -773,6 +774,9 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		const int nd = nrows * VDL2_DUMPS_PER_ROW;
 
 		const float4 *dcorr = kp.dcorr + (size_t) ch * VDL2_DUMPS_PER_ROW;
+		/* phase 2 of the previous item used the stage memory through the generic proxy (its scratch aliases the stages):
+		   order those accesses before the asynchronous-proxy writes of the TMA loads issued below */
+		asm volatile ("fence.proxy.async.shared::cta;":::"memory");
 		if (DP == 2) {
 			/* ---- phase 1, int8 tensor-core mixer: non-overlapping 64-byte boxes, see mix_rows_mma ---- */
 			if (lane == 0) {
@@ -917,7 +921,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				/* wait for the previous tile of this channel, load its state */
 				if (lane == 0) {
 					const volatile int *pr = kp.progress + ch;
-					while (*pr < kp.tile_base + tile)	/* tiles completed since create: launches may overlap */
+					while ((int)((unsigned)(kp.tile_base + tile) - (unsigned)*pr) > 0)	/* tiles completed since create (wrap-safe): launches may overlap */
 						__nanosleep(200);
 				}
 				__syncwarp();
@@ -1043,7 +1047,7 @@ extern "C" int vdl2_kernel_smem_bytes(int nco_entries, int dp4a)
 }
 
 template < int FMT, int DP, bool TAPS > static cudaError_t launch_fmt2(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem,
-									 cudaStream_t st)
+									 cudaStream_t st, int pdl)
 {
 	cudaError_t e = cudaFuncSetAttribute(vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess)
@@ -1058,45 +1062,48 @@ template < int FMT, int DP, bool TAPS > static cudaError_t launch_fmt2(const CUt
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;	/* the next launch may start while this one's tail drains */
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
-	cfg.numAttrs = 1;
+	/* only when the caller asked for overlapping launches AND the operation in front of this one on the stream is a front-end
+	   launch: the kernel never executes griddepcontrol.wait, so anything else in front (the rtl.c expansion kernel, a copy into
+	   the staging buffer) must have completed in the ordinary way before the first TMA load */
+	cfg.numAttrs = pdl ? 1 : 0;
 	return cudaLaunchKernelEx(&cfg, vdl2::vdl2_frontend_kernel < FMT, DP, TAPS >, tmap, kp);
 }
 
-template < int FMT, int DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st)
+template < int FMT, int DP > static cudaError_t launch_fmt(const CUtensorMap & tmap, const Vdl2KParams & kp, int grid, int smem, cudaStream_t st, int pdl)
 {
 #ifdef VDL2_ALWAYS_TAPS
 	if (true)
 #else
 	if (kp.taps || kp.flags)
 #endif
-		return launch_fmt2 < FMT, DP, true > (tmap, kp, grid, smem, st);
-	return launch_fmt2 < FMT, DP, false > (tmap, kp, grid, smem, st);
+		return launch_fmt2 < FMT, DP, true > (tmap, kp, grid, smem, st, pdl);
+	return launch_fmt2 < FMT, DP, false > (tmap, kp, grid, smem, st, pdl);
 }
 
-extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream)
+extern "C" int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream, int pdl)
 {
 	const CUtensorMap & m = *reinterpret_cast < const CUtensorMap * >(tmap);
 	cudaStream_t st = (cudaStream_t) stream;
 	if (dp4a == 2) {
 		switch (fmt) {
-		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 2 > (m, *kp, grid, smem, st);
-		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 2 > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 2 > (m, *kp, grid, smem, st, pdl);
+		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 2 > (m, *kp, grid, smem, st, pdl);
 		}
 		return (int)cudaErrorInvalidValue;
 	}
 	if (dp4a) {
 		switch (fmt) {
-		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 1 > (m, *kp, grid, smem, st);
-		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 1 > (m, *kp, grid, smem, st);
+		case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 1 > (m, *kp, grid, smem, st, pdl);
+		case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 1 > (m, *kp, grid, smem, st, pdl);
 		}
 		return (int)cudaErrorInvalidValue;
 	}
 	switch (fmt) {
-	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 0 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 0 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32, 0 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16, 0 > (m, *kp, grid, smem, st);
-	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL, 0 > (m, *kp, grid, smem, st);
+	case VDL2_FMT_CU8: return (int)launch_fmt < VDL2_FMT_CU8, 0 > (m, *kp, grid, smem, st, pdl);
+	case VDL2_FMT_CS8: return (int)launch_fmt < VDL2_FMT_CS8, 0 > (m, *kp, grid, smem, st, pdl);
+	case VDL2_FMT_CF32: return (int)launch_fmt < VDL2_FMT_CF32, 0 > (m, *kp, grid, smem, st, pdl);
+	case VDL2_FMT_CS16: return (int)launch_fmt < VDL2_FMT_CS16, 0 > (m, *kp, grid, smem, st, pdl);
+	case VDL2_FMT_F32REAL: return (int)launch_fmt < VDL2_FMT_F32REAL, 0 > (m, *kp, grid, smem, st, pdl);
 	}
 	return (int)cudaErrorInvalidValue;
 }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 int vdl2_kernel_smem_bytes(int nco_entries, int dp4a);
-int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream);
+int vdl2_kernel_launch(int fmt, int dp4a, const void *tmap, const Vdl2KParams * kp, int grid, int smem, void *stream, int pdl);
 int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm);
 int vdl2_kernel_upload_tables(const struct Vdl2Tables *t);
 int vdl2_kernel_nsmid(unsigned *d_scratch_word, unsigned *out);

@@ -374,6 +374,8 @@ vdl2_link_kernel(const Vdl2BlockRec * __restrict__ blocks, int nblocks, Vdl2Fram
 		}
 		__syncwarp();
 		ngood = ntotal < MAX_GOOD ? ntotal : MAX_GOOD;
+		if (lane == 0 && ntotal > MAX_GOOD)
+			atomicAdd(nframes + 1, (unsigned)(ntotal - MAX_GOOD));	/* reported by the host as an error: nothing is dropped silently */
 	}
 	/* ---- hand the frames over: hdata[0] = flag, hdata[1..] = ob[n1..], l = closing flag position + 2 ---- */
 	for (int f = 0; f < ngood; f++) {

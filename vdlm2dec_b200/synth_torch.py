@@ -57,9 +57,11 @@ class BurstLibrary:
 
 def make_device_workload(nch: int, nsamples: int, seed: int, device, fs: int = 2_000_000, fos=None,
                          noise_sigma: float = 8.0, gap=(0.15, 0.6), group: int = 16, lib: BurstLibrary | None = None,
-                         fmt: str = "cu8", first_burst=None):
+                         fmt: str = "cu8", first_burst=None, ch_per_stream: int = 1, amp=(25.0, 70.0)):
     """-> (uint8 tensor [nch, 2*nsamples] for cu8, int16 for cs16 (the same signal x 64), list of Fo per channel, number of bursts placed).
-    first_burst: latest start of a channel's first burst in seconds (default 0.25)."""
+    first_burst: latest start of a channel's first burst in seconds (default 0.25).
+    ch_per_stream > 1: `nch` counts STREAMS; every stream carries the bursts of ch_per_stream channels at fos[0 .. ch_per_stream)
+    (the rtl "8 frequencies from one 2 MHz stream" shape, README.md:4); the returned Fo list is per stream-major channel."""
     fos = fos or [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
     lib = lib or BurstLibrary(seed, device, fs)
     out = torch.empty((nch, 2 * nsamples), dtype=torch.uint8 if fmt == "cu8" else torch.int16, device=device)
@@ -67,25 +69,26 @@ def make_device_workload(nch: int, nsamples: int, seed: int, device, fs: int = 2
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + 2)
     nb_total = 0
-    ch_fo = [fos[c % len(fos)] for c in range(nch)]
+    cps = ch_per_stream
+    ch_fo = [fos[c % len(fos)] for c in range(nch)] if cps == 1 else [fos[k] for _ in range(nch) for k in range(cps)]
     for c0 in range(0, nch, group):
         g = min(group, nch - c0)
         x = torch.randn((g, nsamples), dtype=torch.complex64, device=device, generator=gen) * (noise_sigma * math.sqrt(2.0))
-        for i in range(g):
-            fo = ch_fo[c0 + i]
+        for i, k in ((i, k) for i in range(g) for k in range(cps)):
+            fo = ch_fo[(c0 + i) * cps + k]
             t = int(rng.uniform(fs // 1000, (first_burst or 0.25) * fs))
             while True:
                 b, w = lib.items[int(rng.integers(0, len(lib.items)))]
                 L = w.numel()
-                if t + L + 4000 >= nsamples:
+                if t + L + 2 * (fs // 1000) >= nsamples:
                     break
-                amp = float(rng.uniform(25.0, 70.0))
+                a_ = float(rng.uniform(*amp))
                 cfo = float(rng.uniform(-500.0, 500.0))
                 n = torch.arange(t, t + L, dtype=torch.float64, device=device)
                 cyc = (n * ((fo + cfo) / fs)) % 1.0
                 ang = (cyc * (2.0 * math.pi) + float(rng.uniform(0, 2 * math.pi))).to(torch.float32)
                 rot = torch.complex(torch.cos(ang), torch.sin(ang))
-                x[i, t:t + L] += amp * w * rot
+                x[i, t:t + L] += a_ * w * rot
                 nb_total += 1
                 t += L + int(rng.uniform(*gap) * fs)
         iq = torch.view_as_real(x)  # [g, ns, 2]
