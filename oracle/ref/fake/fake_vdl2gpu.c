@@ -133,5 +133,52 @@ int vdl2_drain_frames(vdl2gpu_t * h, vdl2_frame_t * frames, int max_frames, int 
 	return 0;
 }
 
+int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, int max_frames, int *n_frames, uint8_t * bytes, size_t max_bytes, size_t *n_bytes,
+			     vdl2_avlc_t * recs)
+{				/* the same frames, in completion order, packed; field records are not produced by the stand-in */
+	static vdl2_frame_t fr[4096];
+	static vdl2_block_t bl[4096];
+	int nf = 0, nb = 0;
+	(void)recs;
+	*n_frames = 0;
+	*n_bytes = 0;
+	if (vdl2_drain_frames(h, fr, 4096, &nf, bl, 4096, &nb) || nf > max_frames)
+		return 1;
+	int order[4096];
+	for (int i = 0; i < nf; i++)
+		order[i] = i;
+	for (int i = 1; i < nf; i++) {	/* insertion sort by (end of burst, channel, length): a handful of frames per call */
+		int k = order[i], j = i - 1;
+		const int64_t ek = bl[fr[k].block].end_dump;
+		while (j >= 0) {
+			const vdl2_frame_t *a = &fr[order[j]];
+			const int64_t ea = bl[a->block].end_dump;
+			if (ea < ek || (ea == ek && (a->chn < fr[k].chn || (a->chn == fr[k].chn && a->len <= fr[k].len))))
+				break;
+			order[j + 1] = order[j];
+			j--;
+		}
+		order[j + 1] = k;
+	}
+	size_t off = 0;
+	for (int i = 0; i < nf; i++) {
+		const vdl2_frame_t *f = &fr[order[i]];
+		if (off + (size_t) ((f->len + 15) & ~15) > max_bytes)
+			return 1;
+		hdrs[i].sync_dump = f->sync_dump;
+		hdrs[i].chn = f->chn;
+		hdrs[i].Fr = f->Fr;
+		hdrs[i].ppm = f->ppm;
+		hdrs[i].len = f->len;
+		hdrs[i].offset = (uint32_t) off;
+		hdrs[i].dur = (int32_t) (bl[f->block].end_dump - f->sync_dump);
+		memcpy(bytes + off, f->hdata, (size_t) f->len);
+		off += (size_t) ((f->len + 15) & ~15);
+	}
+	*n_frames = nf;
+	*n_bytes = off;
+	return 0;
+}
+
 int vdl2_host_alloc(size_t bytes, void **out) { *out = malloc(bytes); return *out == NULL; }
 int vdl2_host_free(void *p) { free(p); return 0; }

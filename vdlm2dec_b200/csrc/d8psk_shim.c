@@ -51,6 +51,9 @@ static pthread_mutex_t g_busy = PTHREAD_ERRORCHECK_MUTEX_INITIALIZER_NP;
    main.c's signal handler (main.c:106-110) calls exit() on the main thread, which in the replay build is
    the very thread that feeds the GPU: it must not wait for itself (EDEADLK instead of a hang on Ctrl-C). */
 static void deliver(void);
+#ifdef VDL2_SHIM_LINK
+static void out_drain_wait(void);
+#endif
 static int g_last_n;		/* blocks handed over by the last deliver() */
 static double g_first = -1.0, g_last;	/* VDL2_SHIM_STATS: wall clock of the first feed and of the end of the last one */
 static unsigned long long g_fed;
@@ -71,6 +74,9 @@ static void quiesce(void)
 	/* feeds are asynchronous: what the last rounds completed is still on the device.  Collect it, and give the reference's
 	   consumer thread the time to print it before the process goes away (its stopVdlm2() has already returned). */
 	deliver();
+#ifdef VDL2_SHIM_LINK
+	out_drain_wait();	/* the consumer thread has printed everything */
+#endif
 	g_last = now();
 	if (getenv("VDL2_SHIM_STATS") && g_first >= 0)
 		fprintf(stderr, "vdl2gpu shim: fed %llu samples in %.6f s (first feed to last block delivered)\n", g_fed, g_last - g_first);
@@ -112,7 +118,9 @@ int vdl2shim_nch(void)
 /* blocks / frames pending between two drains never exceed the queue, so one drain call always has room */
 #define SHIM_QCAP 4096
 static vdl2_block_t *g_blocks;
-static vdl2_frame_t *g_frames;
+#define SHIM_BYTES ((size_t) SHIM_QCAP * 512)
+static vdl2_frame_hdr_t *g_hdrs;	/* VDL2_SHIM_LINK: packed frames (page-locked) */
+static uint8_t *g_bytes, g_one[2048 + 64];
 static double g_t0 = -1;	/* VDL2_FILE_T0: epoch of sample 0 of a replayed capture; < 0 = wall clock as in d8psk.c:295 */
 
 void vdl2shim_open(unsigned fs, unsigned sdrclk, int format, size_t max_samples)
@@ -130,8 +138,7 @@ void vdl2shim_open(unsigned fs, unsigned sdrclk, int format, size_t max_samples)
 	if (vdl2_create(&cfg, g_par, &g_gpu))
 		die("vdl2_create");
 	g_blocks = malloc(sizeof(vdl2_block_t) * SHIM_QCAP);
-	g_frames = malloc(sizeof(vdl2_frame_t) * SHIM_QCAP);
-	if (!g_blocks || !g_frames) {
+	if (!g_blocks || vdl2_host_alloc(sizeof(vdl2_frame_hdr_t) * SHIM_QCAP, (void **)&g_hdrs) || vdl2_host_alloc(SHIM_BYTES, (void **)&g_bytes)) {
 		fprintf(stderr, "vdl2gpu shim: out of memory\n");
 		exit(1);
 	}
@@ -170,28 +177,102 @@ void stopVdlm2(void)
 {				/* main.c:108,244: nothing is queued on the host */
 }
 
+/* out() runs on its own consumer thread, like the reference's blk_thread (vdlm2.c:84-161, the sole caller of out()): the feeder
+   only copies the packed frames of a drain into a queue entry, so formatting overlaps the next launch instead of delaying it */
+struct outq_entry {
+	struct outq_entry *next;
+	int nf;
+	vdl2_frame_hdr_t *hdrs;
+	uint8_t *bytes;
+};
+static struct outq_entry *q_head, *q_tail;
+static pthread_mutex_t q_mtx = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t q_cond = PTHREAD_COND_INITIALIZER, q_idle = PTHREAD_COND_INITIALIZER;
+static int q_busy, q_started;
+
+static void *out_thread(void *arg)
+{
+	(void)arg;
+	for (;;) {
+		pthread_mutex_lock(&q_mtx);
+		while (!q_head)
+			pthread_cond_wait(&q_cond, &q_mtx);
+		struct outq_entry *e = q_head;
+		q_head = e->next;
+		if (!q_head)
+			q_tail = NULL;
+		q_busy = 1;
+		pthread_mutex_unlock(&q_mtx);
+		for (int i = 0; i < e->nf; i++) {
+			msgblk_t blk;	/* what check_frame() passes on (vdlm2.c:60): only the header fields are read downstream */
+			memset(&blk, 0, sizeof blk);
+			blk.chn = e->hdrs[i].chn;
+			blk.Fr = e->hdrs[i].Fr;
+			blk.ppm = e->hdrs[i].ppm;
+			stamp(&blk.tv, e->hdrs[i].sync_dump);
+			/* out() -> outacars() strips parity bits IN PLACE (outacars.c:223-226) and reads a little past l: own scratch copy */
+			memset(g_one, 0, sizeof g_one);
+			memcpy(g_one, e->bytes + e->hdrs[i].offset, (size_t) e->hdrs[i].len);
+			out(&blk, g_one, e->hdrs[i].len);
+		}
+		free(e->hdrs);
+		free(e->bytes);
+		free(e);
+		pthread_mutex_lock(&q_mtx);
+		q_busy = 0;
+		if (!q_head)
+			pthread_cond_broadcast(&q_idle);
+		pthread_mutex_unlock(&q_mtx);
+	}
+	return NULL;
+}
+
+static void out_drain_wait(void)
+{
+	pthread_mutex_lock(&q_mtx);
+	while (q_head || q_busy)
+		pthread_cond_wait(&q_idle, &q_mtx);
+	pthread_mutex_unlock(&q_mtx);
+}
+
 static void deliver(void)
 {				/* called with g_busy held, after a process call returned */
-	vdl2_frame_t *fr = g_frames;
-	int nf = 0, nb = 0;
-	if (vdl2_drain_frames(g_gpu, fr, SHIM_QCAP, &nf, NULL, 0, &nb))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
-		die("vdl2_drain_frames");
-	for (int i = 0; i < nf; i++) {
-		msgblk_t blk;	/* what check_frame() passes on (vdlm2.c:60): only the header fields are read downstream */
-		memset(&blk, 0, sizeof blk);
-		blk.chn = fr[i].chn;
-		blk.Fr = fr[i].Fr;
-		blk.ppm = fr[i].ppm;
-		stamp(&blk.tv, fr[i].sync_dump);
-		out(&blk, fr[i].hdata, fr[i].len);
+	/* frames leave the device ordered (completion order, the order blk_thread would see the blocks) and packed: a 32-byte
+	   header + the frame's own bytes instead of 2048-byte records (vdl2_drain_frames_packed; page-locked buffers) */
+	int nf = 0;
+	size_t nb = 0;
+	if (vdl2_drain_frames_packed(g_gpu, g_hdrs, SHIM_QCAP, &nf, g_bytes, SHIM_BYTES, &nb, NULL))	/* out*.c reads chn, Fr, ppm, tv only (out.c:169-230,543) */
+		die("vdl2_drain_frames_packed");
+	if (nf == 0)
+		return;
+	struct outq_entry *e = malloc(sizeof *e);
+	e->next = NULL;
+	e->nf = nf;
+	e->hdrs = malloc(sizeof(vdl2_frame_hdr_t) * (size_t) nf);
+	e->bytes = malloc(nb ? nb : 1);
+	memcpy(e->hdrs, g_hdrs, sizeof(vdl2_frame_hdr_t) * (size_t) nf);
+	memcpy(e->bytes, g_bytes, nb);
+	pthread_mutex_lock(&q_mtx);
+	if (!q_started) {
+		pthread_t th;
+		pthread_create(&th, NULL, out_thread, NULL);
+		q_started = 1;
 	}
+	if (q_tail)
+		q_tail->next = e;
+	else
+		q_head = e;
+	q_tail = e;
+	pthread_cond_signal(&q_cond);
+	pthread_mutex_unlock(&q_mtx);
 }
 
 void vdl2shim_finish(void)
-{				/* what the last rounds completed is still on the device */
+{				/* what the last rounds completed is still on the device; then let the consumer print everything */
 	pthread_mutex_lock(&g_busy);
 	deliver();
 	pthread_mutex_unlock(&g_busy);
+	out_drain_wait();
 }
 #else
 static void deliver(void)
@@ -200,7 +281,19 @@ static void deliver(void)
 	int n = 0;
 	if (vdl2_drain_blocks(g_gpu, out, SHIM_QCAP, &n))
 		die("vdl2_drain_blocks");
+	/* the library hands blocks over oldest trigger first; the reference queues a block when its burst ENDS (decodeVdlm2 at the
+	   end of GETFEC, d8psk.c:199-204), so re-order by completion before they reach the single consumer */
+	static int order[SHIM_QCAP];
 	for (int i = 0; i < n; i++) {
+		int j = i - 1;
+		while (j >= 0 && (out[order[j]].end_dump > out[i].end_dump || (out[order[j]].end_dump == out[i].end_dump && out[order[j]].chn > out[i].chn))) {
+			order[j + 1] = order[j];
+			j--;
+		}
+		order[j + 1] = i;
+	}
+	for (int k = 0; k < n; k++) {
+		const int i = order[k];
 		channel_t *ch = NULL;
 		for (int c = 0; c < nbch; c++)
 			if (g_ch[c] && g_ch[c]->chn == out[i].chn)
