@@ -167,6 +167,15 @@ int vdl2_pending_blocks(vdl2gpu_t * h, int *n_out);
 int vdl2_process_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes);
 int vdl2_sync(vdl2gpu_t * h);
 
+/* ---- wideband shared-stream channeliser (generalises d8psk.c:353-381, where every channel
+   thread re-reads the whole Cbuff): ONE pass over each input stream writes the decimated 84 ksps streams (d8psk.c:374-381)
+   of all the channels of the handle that listen to it: d_out[ch * out_pitch + row * 84 + k] = dump k of millisecond `row` of
+   channel ch, as interleaved (re, im) floats; out_pitch counts complex values (even, >= rows * 84).  Device pointers, same
+   input layout as vdl2_process_device(), whole 1 ms rows, 8-bit input at 2 Msps.  No demodulator state is touched;
+   asynchronous on the handle's stream (vdl2_sync); vdl2_stats_t.last_kernel_ms reports its device time.  Every output equals
+   the fused kernel's own decimated stream (tap VDL2_TAP_DUMPS) bit for bit. ---- */
+int vdl2_channelise_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes, float *d_out, size_t out_pitch);
+
 /* completed blocks since the last drain, oldest trigger first (the msgblk_t hand-off) */
 int vdl2_drain_blocks(vdl2gpu_t * h, vdl2_block_t * out, int max, int *n_out);
 

@@ -108,3 +108,44 @@ def test_multi_shared_streams_and_ragged_split():
     m.process(iq)
     got = m.drain_blocks()
     assert len(want) >= nstreams * cps and want.tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("fmt", ["cu8", "cs8"])
+def test_channeliser_one_pass_equals_fused_kernel_and_oracle(fmt):
+    """Row f3 (vdl2_channelise_device): ONE pass over each shared stream yields the decimated streams of all its channels.
+    They must equal the fused kernel's own T1 tap bit for bit (same integer sums) and the oracle's dumps within the T1 bar;
+    3 streams x 8 channels, 70 rows (a ragged last tile)."""
+    import torch
+    from oracle.pyoracle import TAP_DUMPS as O_DUMPS
+    from tests.parity_util import oracle
+    from vdlm2dec_b200 import synth
+    from vdlm2dec_b200.api import TAP_DUMPS
+    cps, nstreams, rows = 8, 3, 70
+    n = rows * 2000
+    fos = [-450_000, -325_000, -200_000, -75_000, 50_000, 175_000, 300_000, 425_000]
+    rng = np.random.default_rng(8)
+    iq = []
+    for s in range(nstreams):
+        x = 3.0 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        for k, fo in enumerate(fos):
+            spec = synth.standard_channel(seed=800 + 10 * s + k, nsamples=n, Fo=fo, period=40_000, amp=(12.0, 16.0), noise_sigma=0.0)
+            x += synth.render_channel(spec, n, fmt="cf32").astype(np.float64).view(np.complex128)
+        iq.append(synth.quantise(x, fmt))
+    iq = np.stack(iq)
+    chans = [(s * cps + k, 136_000_000 + fos[k] % 1_000_000, fos[k]) for s in range(nstreams) for k in range(cps)]
+    g = Vdl2Gpu(chans, fmt=fmt, ch_per_stream=cps, taps=TAP_DUMPS, max_samples=n)
+    t = torch.from_numpy(iq.view(np.uint8)).cuda()
+    out = torch.zeros((len(chans), rows * 84 + 4), dtype=torch.complex64, device="cuda")
+    g.channelise_device(t.data_ptr(), n, t.stride(0), out.data_ptr(), out.stride(0))
+    g.sync()
+    assert g.stats()["last_kernel_ms"] > 0
+    got = out.cpu().numpy()
+    assert (got[:, rows * 84:] == 0).all()             # nothing written past the last row
+    g.process(iq)                                       # the fused kernel on the same samples, with its T1 tap
+    for c, (chn, Fr, fo) in enumerate(chans):
+        tap = g.read_dumps(c)
+        assert len(tap) == rows * 84 and tap.view(np.uint32).tolist() == got[c, :rows * 84].view(np.uint32).tolist(), f"channel {c}"
+        if c % 5 == 0:
+            want = oracle(chn=chn, Fr=Fr, Fo=fo, taps=O_DUMPS).feed(iq[c // cps], fmt).dumps
+            rms = np.sqrt(np.mean(np.abs(want) ** 2))
+            assert np.abs(want - got[c, :rows * 84]).max() < 1e-5 * rms

@@ -76,6 +76,35 @@ for nch in (32, 64, 128, 256, 512, 1024, 2048, 4096):
     run(nch, ns if nch <= 2048 else ns // 2, label="config 3 curve: 1 channel per stream, 2 Msps cu8, bursts")
 run(8, ns, cps=8, label="config 2: 8 channels from one 2 Msps cu8 stream")
 run(1024, ns, cps=8, label="128 streams x 8 channels")
+def run_f3(nstreams, cps, ns, reps=4):
+    """row f3: the one-pass channeliser (decimated streams of all channels of every stream to HBM) next to the fused kernel's phase-1 share"""
+    raster = [f for f in range(-450_000, 475_000, 125_000) if abs(f) >= 50_000]
+    x, fos, nb = make_device_workload(nstreams, ns, seed=1000, device=dev, fos=raster, ch_per_stream=cps, amp=(12.0, 18.0))
+    nch = nstreams * cps
+    chans = [(c, 136_000_000 + fos[c] % 1_000_000, fos[c]) for c in range(nch)]
+    g = Vdl2Gpu(chans, ch_per_stream=cps, max_samples=ns)
+    rows = ns // 2000
+    outb = torch.empty((nch, rows * 84), dtype=torch.complex64, device=dev)
+    ms = []
+    for _ in range(reps):
+        g.channelise_device(x.data_ptr(), ns, x.stride(0), outb.data_ptr(), outb.stride(0))
+        g.sync()
+        ms.append(g.stats()["last_kernel_ms"])
+    t = float(np.median(ms[1:]))
+    bytes_in, bytes_out = nstreams * ns * 2, nch * rows * 84 * 8
+    rec = {"label": f"row f3: one-pass channeliser, {nstreams} streams x {cps} channels, 2 Msps cu8 -> 84 ksps complex float", "channels": nch, "ch_per_stream": cps,
+           "samples_per_channel": ns, "kernel_ms": round(t, 4), "msamples_per_s": round(nch * ns / t / 1e3, 1), "bytes_in": bytes_in, "bytes_out": bytes_out,
+           "hbm_gbs_algorithmic": round((bytes_in + bytes_out) / t / 1e6, 1), "frac_of_hbm_peak": round((bytes_in + bytes_out) / t / 1e6 / peak, 4)}
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+    g.close()
+    del x, outb
+    torch.cuda.empty_cache()
+
+
+run_f3(128, 8, ns)
+run_f3(1024, 1, ns)
+run_f3(1, 8, ns)
 # BASELINE config 5 ("Airspy 10 Msps cs16, 8 channels, FIR-tap length sweep 64 -> 512"): the reference's channel filter is the boxcar over
 # one dump, fs / 84000 samples long, so the sweep with an oracle is the rate sweep fs = 84 kHz x L (DESIGN.md section 9)
 for L in (75, 125, 250, 500):

@@ -72,7 +72,7 @@ EXPORTS = ["vdl2_abi_version", "vdl2_last_error", "vdl2_create", "vdl2_destroy",
            "vdl2_process_device", "vdl2_sync", "vdl2_drain_blocks", "vdl2_read_dumps", "vdl2_read_steps",
            "vdl2_read_syncs", "vdl2_read_syms", "vdl2_get_stats", "vdl2_cuda_stream", "vdl2_link_decode",
            "vdl2_drain_frames", "vdl2_host_alloc", "vdl2_host_free", "vdl2_process_host_rtl", "vdl2_avlc_extract",
-           "vdl2_submit_host", "vdl2_submit_copy", "vdl2_pending_blocks", "vdl2_drain_frames_packed", "vdl2_last_pack_ms",
+           "vdl2_submit_host", "vdl2_submit_copy", "vdl2_pending_blocks", "vdl2_drain_frames_packed", "vdl2_last_pack_ms", "vdl2_channelise_device",
            "vdl2_multi_create", "vdl2_multi_destroy", "vdl2_multi_process_host", "vdl2_multi_drain_blocks", "vdl2_multi_ndev",
            "vdl2_multi_handle", "vdl2_multi_last_error"]
 
@@ -100,6 +100,7 @@ def load_library():
     lib.vdl2_pending_blocks.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     lib.vdl2_drain_frames_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t,
                                              C.POINTER(C.c_size_t), C.c_void_p]
+    lib.vdl2_channelise_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
     lib.vdl2_last_pack_ms.restype = C.c_float
     lib.vdl2_last_pack_ms.argtypes = [C.c_void_p]
     lib.vdl2_multi_create.argtypes = [C.POINTER(Config), C.POINTER(ChanParam), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
@@ -209,6 +210,11 @@ class Vdl2Gpu:
     def process_device(self, dev_ptr: int, nsamples: int, pitch_bytes: int):
         """Device-resident input (e.g. a torch tensor's data_ptr()); asynchronous, see sync()."""
         self._check(self.lib.vdl2_process_device(self.h, C.c_void_p(dev_ptr), nsamples, pitch_bytes))
+
+    def channelise_device(self, dev_ptr: int, nsamples: int, pitch_bytes: int, out_ptr: int, out_pitch: int):
+        """Row f3: one pass over every stream -> decimated 84 ksps streams of all channels at out_ptr (device, complex64
+        [nch, out_pitch]); asynchronous."""
+        self._check(self.lib.vdl2_channelise_device(self.h, C.c_void_p(dev_ptr), nsamples, pitch_bytes, C.c_void_p(out_ptr), out_pitch))
 
     def sync(self):
         self._check(self.lib.vdl2_sync(self.h))

@@ -97,7 +97,7 @@ struct vdl2gpu {
 	/* packed drain (vdl2_drain_frames_packed): rank / offsets / headers / bytes / records on the device, totals in page-locked memory */
 	int *d_rank;
 	unsigned *d_offs, *d_totals;
-	void *d_hdrs, *d_precs;
+	void *d_hdrs, *d_precs, *d_keys;
 	uint8_t *d_pbytes;
 	int pack_cap;
 	unsigned *h_totals;
@@ -647,6 +647,7 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaFree(h->d_totals);
 	cudaFree(h->d_hdrs);
 	cudaFree(h->d_precs);
+	cudaFree(h->d_keys);
 	cudaFree(h->d_pbytes);
 	if (h->h_totals)
 		cudaFreeHost(h->h_totals);
@@ -699,9 +700,13 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 		   start of a dump (TMA boxes must start 16-byte aligned), 64B-swizzled; samples past the end of a row read as zero */
 		const cuuint64_t dims[3] = { (cuuint64_t) h->row_samples, (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
 		const cuuint32_t box[3] = { 32, 32, 1 };
+		/* L2 promotion 128 B: measured DRAM traffic per bench step 9.07 GB (1.056 x algorithmic) against 9.61 GB with 256 B, 9.22 GB
+		   without and 9.05 GB with 64 B (the latter 6 % slower); profiles/r2_promo_ab.txt */
+		CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+		if (const char *pe = getenv("VDL2_TMA_PROMO"))	/* A/B: 0 none, 1 64 B, 2 128 B, 3 256 B */
+			promo = (CUtensorMapL2promotion) atoi(pe);
 		r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)base, dims, strides, box, estr,
-						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-						    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+						    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	} else {
 		const cuuint64_t dims[3] = { (cuuint64_t) (h->row_bytes / 4), (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
 		const cuuint32_t box[3] = { 32, 32, 1 };
@@ -968,6 +973,47 @@ extern "C" int vdl2_process_device(vdl2gpu_t * h, const void *d_iq, size_t nsamp
 		CK(h, cudaMemcpy2DAsync(h->d_stage + h->carry * bps, h->stage_pitch, d_iq, h->nstreams > 1 ? pitch_bytes : nsamples * bps,
 					nsamples * bps, h->nstreams, cudaMemcpyDeviceToDevice, h->stream));
 	return run_staged(h, h->carry + nsamples);
+}
+
+/* ---- row f3: wideband shared-stream channeliser (vdl2_channelise_kernel).  One pass over every input stream writes the
+   decimated 84 ksps streams (d8psk.c:374-381, tap T1) of ALL the channels demodulated from it; no demodulator state is touched.
+   8-bit input at 2 Msps only (the tensor-core mixer's tables); whole 1 ms rows. ---- */
+extern "C" int vdl2_channelise_device(vdl2gpu_t * h, const void *d_iq, size_t nsamples, size_t pitch_bytes, float *d_out, size_t out_pitch)
+{
+	if (!h || !d_iq || !d_out)
+		return fail(h, "vdl2_channelise_device: null argument");
+	if (h->dp4a != 2)
+		return fail(h, "vdl2_channelise_device: needs 8-bit input at 2 Msps (the tensor-core mixer)");
+	if (nsamples == 0 || nsamples % h->row_samples)
+		return fail(h, "vdl2_channelise_device: %zu samples are not whole 1 ms rows", nsamples);
+	const int nrows = (int)(nsamples / h->row_samples);
+	if (out_pitch < (size_t) nrows * VDL2_DUMPS_PER_ROW || (out_pitch & 1) || ((uintptr_t) d_out & 15))
+		return fail(h, "vdl2_channelise_device: output pitch %zu too small / odd, or output not 16-byte aligned", out_pitch);
+	const size_t pitch = h->nstreams == 1 ? (size_t) h->row_bytes * nrows : pitch_bytes;
+	if (((uintptr_t) d_iq & 15) || (pitch & 15))
+		return fail(h, "vdl2_channelise_device: input base/pitch must be 16-byte aligned for TMA");
+	CK(h, cudaSetDevice(h->cfg.device));
+	CUtensorMap tmap;
+	const cuuint64_t dims[3] = { (cuuint64_t) h->row_samples, (cuuint64_t) nrows, (cuuint64_t) h->nstreams };
+	const cuuint64_t strides[2] = { (cuuint64_t) h->row_bytes, (cuuint64_t) pitch };
+	const cuuint32_t box[3] = { 32, 32, 1 }, estr[3] = { 1, 1, 1 };
+	const CUresult r = ((encode_tiled_t) h->encode_fn) (&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)d_iq, dims, strides, box, estr,
+							   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+							   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+		return fail(h, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+	const long long items = (long long)((nrows + VDL2_ROWS_PER_TILE - 1) / VDL2_ROWS_PER_TILE) * h->nstreams;
+	const int grid = (int)std::min < long long >(items, (long long)h->n_sm * 16);
+	CK(h, cudaMemsetAsync(h->d_ticket + 11, 0, 4, h->stream));
+	CK(h, cudaEventRecord(h->ev0, h->stream));
+	const cudaError_t e = (cudaError_t) vdl2_channelise_launch(h->cfg.format, &tmap, h->nstreams, h->cfg.ch_per_stream, nrows, h->nbox, h->sched_slot, h->d_w8,
+								  h->d_dcorr, d_out, out_pitch, h->d_ticket + 11, grid, h->stream);
+	if (e != cudaSuccess)
+		return fail(h, "channeliser launch failed: %s", cudaGetErrorString(e));
+	CK(h, cudaEventRecord(h->ev1, h->stream));
+	h->ev_valid = true;
+	h->last_was_launch = false;
+	return 0;
 }
 
 extern "C" int vdl2_sync(vdl2gpu_t * h)
@@ -1246,7 +1292,9 @@ extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, 
 		cudaFree(h->d_offs);
 		cudaFree(h->d_hdrs);
 		cudaFree(h->d_precs);
+		cudaFree(h->d_keys);
 		cudaFree(h->d_pbytes);
+		h->d_keys = NULL;
 		h->d_rank = NULL;
 		h->d_offs = NULL;
 		h->d_hdrs = h->d_precs = NULL;
@@ -1256,6 +1304,7 @@ extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, 
 		CK(h, cudaMalloc(&h->d_offs, sizeof(unsigned) * (size_t) fcap));
 		CK(h, cudaMalloc(&h->d_hdrs, 32 * (size_t) fcap));
 		CK(h, cudaMalloc(&h->d_precs, sizeof(vdl2_avlc_t) * (size_t) fcap));
+		CK(h, cudaMalloc(&h->d_keys, 16 * (size_t) fcap));
 		CK(h, cudaMalloc(&h->d_pbytes, (size_t) 2032 * fcap));	/* worst case: every frame 2016 bytes + padding */
 		h->pack_cap = fcap;
 	}
@@ -1277,7 +1326,7 @@ extern "C" int vdl2_drain_frames_packed(vdl2gpu_t * h, vdl2_frame_hdr_t * hdrs, 
 	CK(h, cudaEventRecord(h->pev0, h->stream));
 	e = (cudaError_t) vdl2_frames_pack_launch(h->d_frames, h->d_nframes, cap, h->d_rank, h->d_offs, h->d_totals, h->d_hdrs, h->d_pbytes,
 						  (unsigned)std::min < size_t > ((size_t) 2032 * h->pack_cap, 0xffffffffu), recs ? h->d_precs : NULL,
-						  (int)std::min < unsigned >(4 * n, cap), h->stream);
+						  (int)std::min < unsigned >(4 * n, cap), h->d_keys, h->stream);
 	if (e != cudaSuccess)
 		return fail(h, "frame packing launch failed: %s", cudaGetErrorString(e));
 	CK(h, cudaEventRecord(h->pev1, h->stream));

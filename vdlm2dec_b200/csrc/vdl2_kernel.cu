@@ -505,6 +505,17 @@ template < int FMT > __device__ __forceinline__ void imma_16832(int (&c)[4], con
 			      "+r"(c[1]), "+r"(c[2]), "+r"(c[3]):"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+/* first k step of a dump: D = A B + (cx, cy, cx, cy), the accumulator start values straight from the table registers (no copies) */
+template < int FMT > __device__ __forceinline__ void imma_16832_init(int (&d)[4], const uint32_t(&a)[4], uint32_t b0, uint32_t b1, int cx, int cy)
+{
+	if (FMT == VDL2_FMT_CU8)
+		asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};":"=r" (d[0]),
+			      "=r"(d[1]), "=r"(d[2]), "=r"(d[3]):"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(cx), "r"(cy));
+	else
+		asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};":"=r" (d[0]),
+			      "=r"(d[1]), "=r"(d[2]), "=r"(d[3]):"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(cx), "r"(cy));
+}
+
 __device__ __forceinline__ void ldsm_x4(uint32_t(&a)[4], uint32_t addr)
 {
 	asm volatile ("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];":"=r" (a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]):"r"(addr));
@@ -523,6 +534,16 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n)
 	uint32_t r;
 	asm("shr.u32 %0, %1, %2;":"=r"(r):"r"(v), "r"(n));
 	return r;
+}
+
+/* 16-byte read-only load with an L2 eviction hint: the per-channel tables (9 KB per channel, re-read for every tile of the
+   channel) are kept with evict_last -- without it the streaming input pushes them out and they come back from DRAM
+   (0.63 GB of 9.3 GB read per step in the round-2 v15 profile) */
+__device__ __forceinline__ uint4 ldg_keep(const void *p, unsigned long long policy)
+{
+	uint4 v;
+	asm volatile ("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;":"=r" (v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w):"l"(p), "l"(policy));
+	return v;
 }
 
 /* one elected lane (the warp is converged): lets ptxas issue the TMA from uniform registers without a broadcast loop */
@@ -573,7 +594,7 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	const float2 sc = make_float2(scx, scy), nsc = make_float2(nscx, nscy);
 	const int nbox = kp.nbox;
 	int st = 0, box = 0;
-	int4 dn = __ldg(dp);
+	uint4 dn = ldg_keep(dp, l2keep);
 	mbar_wait(smem_u32(bars), phases & 1u);
 	phases ^= 1u;
 	static_assert(VDL2_DUMPS_PER_ROW % MM_UNROLL == 0 && (MM_NST & (MM_NST - 1)) == 0, "whole store groups per row; ring size a power of two");
@@ -588,10 +609,10 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 		int rst[MM_UNROLL], rbox[MM_UNROLL];	/* stage / box to refill after the dump (-1: none) */
 #pragma unroll
 		for (int u = 0; u < MM_UNROLL; u++) {
-			dc[u] = dn;
+			dc[u] = make_int4((int)dn.x, (int)dn.y, (int)dn.z, (int)dn.w);
 			const unsigned sk = sched[dk0 + u];
 			dp += 4;
-			dn = __ldg(dp);	/* the table carries one entry more than there are dumps */
+			dn = ldg_keep(dp, l2keep);	/* the table carries one entry more than there are dumps */
 			const int st1 = (st + 1) & (MM_NST - 1);
 			if (sk & VDL2_MM_W) {
 				mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
@@ -624,9 +645,9 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 		float2 out[MM_UNROLL];
 #pragma unroll
 		for (int u = 0; u < MM_UNROLL; u++) {
-			int c0[4] = { dc[u].x, dc[u].y, dc[u].x, dc[u].y }, c1[4] = { dc[u].x, dc[u].y, dc[u].x, dc[u].y };
-			imma_16832 < FMT > (c0, a00[u], B[u].x, B[u].y);
-			imma_16832 < FMT > (c1, a10[u], B[u].x, B[u].y);
+			int c0[4], c1[4];
+			imma_16832_init < FMT > (c0, a00[u], B[u].x, B[u].y, dc[u].x, dc[u].y);
+			imma_16832_init < FMT > (c1, a10[u], B[u].x, B[u].y, dc[u].x, dc[u].y);
 			imma_16832 < FMT > (c0, a01[u], B[u].z, B[u].w);
 			imma_16832 < FMT > (c1, a11[u], B[u].z, B[u].w);
 			if (rst[u] >= 0) {	/* the products above consumed the window: ldmatrix has completed for the whole warp */
@@ -788,7 +809,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 			}
 			uint4 *btsm = reinterpret_cast < uint4 * >(wsm);
 			for (int i = lane; i < VDL2_MM_BT_ENTRIES; i += 32)
-				btsm[i] = __ldg(kp.w8 + (size_t) ch * VDL2_MM_BT_ENTRIES + i);
+				btsm[i] = ldg_keep(kp.w8 + (size_t) ch * VDL2_MM_BT_ENTRIES + i, l2keep);
 			__syncwarp();
 			mix_rows_mma < FMT > (&tmap, kp, stage0, bars, btsm, phases, row0, stream,
 					      reinterpret_cast < const int4 * >(kp.dcorr) + (size_t) ch * VDL2_MM_DT_ENTRIES, sd, l2pol, l2keep);
@@ -1026,6 +1047,153 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	}
 }
 
+/* ------------------------------------------------------------------ row f3: wideband shared-stream channeliser
+ *
+ * One pass over a stream produces the decimated 84 ksps streams of ALL its channels (generalises d8psk.c:353-381, where every
+ * channel thread re-reads the whole Cbuff): the raw bytes of a dump window go through ldmatrix ONCE and are multiplied by the
+ * weight fragments of every channel in turn.  In tensor-core terms the channel axis is simply more columns of B --
+ * C[32 rows x 8 nch] = A[32 x 64] * B[64 x 8 nch] -- i.e. a pruned DFT whose "bins" are the reference's own oscillator
+ * tables, so every output is the SAME exact integer sum as in the fused kernel (bit-identical to its T1 tap).
+ * Items are (tile, stream); weights and per-dump constants come straight from L2 (they are shared by every warp working on
+ * the stream, 9 KB per channel), outputs go to HBM in time order: out[channel][row * 84 + dump].
+ */
+struct Vdl2ChanlParams {
+	int nstreams, cps, nrows, ntiles, nbox, sched_slot;
+	const uint4 *bt;	/* [nch][VDL2_MM_BT_ENTRIES] */
+	const int4 *dt;		/* [nch][VDL2_MM_DT_ENTRIES] */
+	float2 *out;		/* [nch][out_pitch] */
+	size_t out_pitch;	/* float2 per channel */
+	unsigned *ticket;
+};
+
+template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_kernel(const __grid_constant__ CUtensorMap tmap, const Vdl2ChanlParams cp)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const int lane = threadIdx.x;
+	unsigned char *stage0 = smem;
+	unsigned long long *bars = reinterpret_cast < unsigned long long *>(smem + MM_NST * MM_STAGE);
+	if (lane == 0) {
+		for (int s = 0; s < MM_NST; s++)
+			mbar_init(smem_u32(bars + s), 1);
+		asm volatile ("fence.mbarrier_init.release.cluster;":::"memory");
+	}
+	__syncwarp();
+	unsigned long long l2pol;
+	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
+	const unsigned *sched = c_tab.sched_slots[cp.sched_slot];
+	const int g = lane >> 2, t = lane & 3;
+	const uint32_t sw16 = ((uint32_t) (lane >> 1) & 3u) << 4, cwl16 = ((uint32_t) lane >> 4) << 4;
+	const uint32_t rowoff = smem_u32(stage0) + (((uint32_t) lane >> 3) & 1u) * 512u + ((uint32_t) lane & 7u) * 64u;
+	const int btl = ((g >> 2) * 3 + min(g & 3, 2)) * 4 + t;
+	const float2 sc = (t & 1) ? make_float2(1.f, 0.f) : make_float2(65536.f, 256.f);
+	const float2 nsc = make_float2(-12582912.f * sc.x, -12582912.f * sc.y);
+	const int t32 = 32 * t;
+	const bool odd = (t & 1) != 0, hi = (t >> 1) != 0;
+	const int rowl = g + 16 * (t & 1) + 8 * (t >> 1);	/* the row this lane owns after the two exchanges */
+	uint32_t phases = 0;
+	const int nitems = cp.ntiles * cp.nstreams;
+	for (;;) {
+		int item = 0;
+		if (lane == 0)
+			item = (int)atomicAdd(cp.ticket, 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= nitems)
+			break;
+		const int tile = item / cp.nstreams, stream = item - tile * cp.nstreams;
+		const int row0 = tile * VDL2_ROWS_PER_TILE;
+		const bool rowok = row0 + rowl < cp.nrows;
+		asm volatile ("fence.proxy.async.shared::cta;":::"memory");
+		if (lane == 0)
+			for (int b = 0; b < MM_NST; b++) {
+				const uint32_t bar = smem_u32(bars + b);
+				mbar_expect_tx(bar, MM_STAGE);
+				tma_load_3d(smem_u32(stage0 + b * MM_STAGE), &tmap, bar, b * 32, row0, stream, l2pol);
+			}
+		int st = 0, box = 0;
+		mbar_wait(smem_u32(bars), phases & 1u);
+		phases ^= 1u;
+#pragma unroll 1
+		for (int dk0 = 0; dk0 < VDL2_DUMPS_PER_ROW; dk0 += 2) {
+			uint32_t a00[2][4], a01[2][4], a10[2][4], a11[2][4];
+			unsigned skv[2];
+			int rst[2], rbox[2];
+#pragma unroll
+			for (int u = 0; u < 2; u++) {
+				const unsigned sk = sched[dk0 + u];
+				skv[u] = sk;
+				const int st1 = (st + 1) & (MM_NST - 1);
+				if (sk & VDL2_MM_W) {
+					mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
+					phases ^= 1u << st1;
+				}
+				const uint32_t base0 = rowoff + (uint32_t) st * MM_STAGE, base1 = rowoff + (uint32_t) st1 * MM_STAGE;
+				const uint32_t q0 = (sk & 0x30u) + cwl16, q1 = q0 + 32u;
+				const uint32_t ad0 = (q0 >= 64u ? base1 : base0) + ((q0 ^ sw16) & 0x30u);
+				const uint32_t ad1 = (q1 >= 64u ? base1 : base0) + ((q1 ^ sw16) & 0x30u);
+				ldsm_x4(a00[u], ad0);
+				ldsm_x4(a10[u], ad0 + 1024u);
+				ldsm_x4(a01[u], ad1);
+				ldsm_x4(a11[u], ad1 + 1024u);
+				rst[u] = -1;
+				rbox[u] = 0;
+				if (sk & VDL2_MM_R) {
+					if (box + MM_NST < cp.nbox) {
+						rst[u] = st;
+						rbox[u] = box + MM_NST;
+					}
+					box++;
+					st = st1;
+				}
+			}
+			/* the windows are in registers: every channel of the stream takes its turn with its own weights */
+#pragma unroll 1
+			for (int c = 0; c < cp.cps; c++) {
+				const int ch = stream * cp.cps + c;
+				const uint4 *bt = cp.bt + (size_t) ch * VDL2_MM_BT_ENTRIES + btl;
+				const int4 *dt = cp.dt + (size_t) ch * VDL2_MM_DT_ENTRIES + dk0 * 4 + t;
+				float2 o[2];
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const unsigned sk = skv[u];
+					uint4 B = __ldg(bt + ((sk & 0x3f00u) >> 6));	/* 6 p * 4 entries of 16 bytes */
+					const int4 dc = __ldg(dt + 4 * u);
+					const int o16 = (int)((sk >> 16) & 127u), te = t32 - (int)(sk >> 23);
+					B.x &= shl_clamp(0xffffffffu, (uint32_t) max(o16 - t32, 0));
+					B.z &= shr_clamp(0xffffffffu, (uint32_t) max(te + 288, 0));
+					B.w &= shr_clamp(0xffffffffu, (uint32_t) max(te + 416, 0));
+					int c0[4], c1[4];
+					imma_16832_init < FMT > (c0, a00[u], B.x, B.y, dc.x, dc.y);
+					imma_16832_init < FMT > (c1, a10[u], B.x, B.y, dc.x, dc.y);
+					imma_16832 < FMT > (c0, a01[u], B.z, B.w);
+					imma_16832 < FMT > (c1, a11[u], B.z, B.w);
+					const float2 y0 = ffma2(make_float2(__int_as_float(c0[0]), __int_as_float(c0[1])), sc, nsc);
+					const float2 y1 = ffma2(make_float2(__int_as_float(c0[2]), __int_as_float(c0[3])), sc, nsc);
+					const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
+					const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
+					const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;
+					const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
+					const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
+					const float sf = __int_as_float(dc.z), corr = __int_as_float(dc.w);
+					const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
+					const float rx = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 2);
+					o[u] = make_float2(hi ? rx : v0, hi ? v1 : rx);
+				}
+				if (rowok)
+					__stcs(reinterpret_cast < float4 * >(cp.out + (size_t) ch * cp.out_pitch + (size_t) (row0 + rowl) * VDL2_DUMPS_PER_ROW + dk0),
+					       make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+			}
+			__syncwarp();
+#pragma unroll
+			for (int u = 0; u < 2; u++)
+				if (rst[u] >= 0 && elect_one()) {
+					const uint32_t bar = smem_u32(bars + rst[u]);
+					mbar_expect_tx(bar, MM_STAGE);
+					tma_load_3d(smem_u32(stage0 + rst[u] * MM_STAGE), &tmap, bar, rbox[u] * 32, row0, stream, l2pol);
+				}
+		}
+	}
+}
+
 /* highest SM id + 1 (ids are not contiguous on parts with disabled SMs): sizes the scratch and the slot masks */
 __global__ void vdl2_nsmid_kernel(unsigned *out)
 {
@@ -1145,6 +1313,32 @@ extern "C" int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_
 	case VDL2_FMT_F32REAL: return (int)occ_fmt < VDL2_FMT_F32REAL, 0 > (smem, ctas_per_sm);
 	}
 	return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int vdl2_channelise_launch(int fmt, const void *tmap, int nstreams, int cps, int nrows, int nbox, int sched_slot, const void *bt, const void *dt,
+				      void *out, size_t out_pitch, unsigned *ticket, int grid, void *stream)
+{
+	vdl2::Vdl2ChanlParams cp;
+	cp.nstreams = nstreams;
+	cp.cps = cps;
+	cp.nrows = nrows;
+	cp.ntiles = (nrows + VDL2_ROWS_PER_TILE - 1) / VDL2_ROWS_PER_TILE;
+	cp.nbox = nbox;
+	cp.sched_slot = sched_slot;
+	cp.bt = (const uint4 *)bt;
+	cp.dt = (const int4 *)dt;
+	cp.out = (float2 *) out;
+	cp.out_pitch = out_pitch;
+	cp.ticket = ticket;
+	const CUtensorMap & m = *reinterpret_cast < const CUtensorMap * >(tmap);
+	const int smem = MM_NST * MM_STAGE + 64;
+	if (fmt == VDL2_FMT_CU8)
+		vdl2::vdl2_channelise_kernel < VDL2_FMT_CU8 > <<<grid, 32, smem, (cudaStream_t) stream >>> (m, cp);
+	else if (fmt == VDL2_FMT_CS8)
+		vdl2::vdl2_channelise_kernel < VDL2_FMT_CS8 > <<<grid, 32, smem, (cudaStream_t) stream >>> (m, cp);
+	else
+		return (int)cudaErrorInvalidValue;
+	return (int)cudaGetLastError();
 }
 
 extern "C" int vdl2_kernel_nsmid(unsigned *d_scratch_word, unsigned *out)

@@ -28,6 +28,9 @@ int vdl2_kernel_occupancy(int fmt, int dp4a, int smem, int *ctas_per_sm);
 int vdl2_kernel_upload_tables(const struct Vdl2Tables *t);
 int vdl2_kernel_nsmid(unsigned *d_scratch_word, unsigned *out);
 int vdl2_kernel_upload_sched(int slot, const unsigned *sched);
+/* row f3 (vdl2_channelise_kernel): one pass over every stream -> the decimated streams of all its channels */
+int vdl2_channelise_launch(int fmt, const void *tmap, int nstreams, int cps, int nrows, int nbox, int sched_slot, const void *bt, const void *dt,
+			   void *out, size_t out_pitch, unsigned *ticket, int grid, void *stream);
 #ifdef __cplusplus
 }
 #endif

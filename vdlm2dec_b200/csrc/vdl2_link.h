@@ -28,7 +28,7 @@ int vdl2_avlc_launch(const Vdl2FrameRec * d_frames, int nframes, void *d_recs, v
 /* frames (unordered, count on the device) -> completion-order rank, 16-byte aligned offsets, 32-byte headers + packed bytes,
    field records in the same order; d_totals[0] = frames, [1] = bytes.  expect = host-side upper bound of the frame count */
 int vdl2_frames_pack_launch(const Vdl2FrameRec * d_frames, const unsigned *d_nframes, unsigned cap, int *d_rank, unsigned *d_offs,
-			    unsigned *d_totals, void *d_hdrs, uint8_t * d_bytes, unsigned bytes_cap, void *d_recs, int expect, void *stream);
+			    unsigned *d_totals, void *d_hdrs, uint8_t * d_bytes, unsigned bytes_cap, void *d_recs, int expect, void *d_keys, void *stream);
 #ifdef __cplusplus
 }
 #endif
