@@ -72,6 +72,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * ma
 		      :"memory");
 }
 
+/* TMA prefetch of a box into L2 (no shared memory, no barrier; SASS UTMAPF): would raise the bytes in flight per warp beyond
+   what the stage ring holds.  Tried in round 2 (MM_PREFETCH) on the theory that 16 one-warp CTAs per SM with a few KB in flight
+   each cannot cover the DRAM latency -- measured 19-24 % SLOWER at every distance, so it is compiled out. */
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap * map, int c0, int c1, int c2)
+{
+	asm volatile ("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"::"l" (map), "r"(c0), "r"(c1), "r"(c2):"memory");
+}
+
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {
 	unsigned long long ra = *reinterpret_cast < unsigned long long *>(&a);
@@ -491,6 +499,9 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
  */
 #define MM_NST VDL2_MM_NST
 #define MM_STAGE 2048		/* 32 rows x 64 bytes */
+#ifndef MM_PREFETCH
+#define MM_PREFETCH 0		/* boxes prefetched into L2 ahead of the stage ring: A/B on B200 (profiles/r2_ab_prefetch.txt): 0 -> 2.69 ms, 8 -> 3.20, 16 -> 3.26, 24 -> 3.34 ms per step: off */
+#endif
 #ifndef MM_UNROLL
 #define MM_UNROLL 2		/* dumps per store group: 2 = half a 32-byte sector per lane and store (A/B on B200: 1 % faster than 4, smaller loop) */
 #endif
@@ -656,6 +667,8 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 					const uint32_t bar = smem_u32(bars + rst[u]);
 					mbar_expect_tx(bar, MM_STAGE);
 					tma_load_3d(smem_u32(stage0 + rst[u] * MM_STAGE), tmap, bar, rbox[u] * 32, row0, stream, l2pol);
+					if (MM_PREFETCH && rbox[u] + MM_PREFETCH < nbox)
+						tma_prefetch_3d(tmap, (rbox[u] + MM_PREFETCH) * 32, row0, stream);
 				}
 			}
 			/* the accumulators are floats 12582912 + sum: remove the bias and weigh the digits in one exact FFMA2 each */
@@ -806,6 +819,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 					mbar_expect_tx(bar, MM_STAGE);
 					tma_load_3d(smem_u32(stage0 + b * MM_STAGE), &tmap, bar, b * 32, row0, stream, l2pol);
 				}
+				for (int b = MM_NST; b < MM_NST + MM_PREFETCH; b++)
+					tma_prefetch_3d(&tmap, b * 32, row0, stream);
 			}
 			uint4 *btsm = reinterpret_cast < uint4 * >(wsm);
 			for (int i = lane; i < VDL2_MM_BT_ENTRIES; i += 32)
@@ -1110,6 +1125,13 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 				tma_load_3d(smem_u32(stage0 + b * MM_STAGE), &tmap, bar, b * 32, row0, stream, l2pol);
 			}
 		int st = 0, box = 0;
+		uint4 Bn[2];
+		int4 dcn[2];
+#pragma unroll
+		for (int u = 0; u < 2; u++) {	/* weights / constants of (pair 0, channel 0) */
+			Bn[u] = __ldg(cp.bt + (size_t) (stream * cp.cps) * VDL2_MM_BT_ENTRIES + btl + ((sched[u] & 0x3f00u) >> 6));
+			dcn[u] = __ldg(cp.dt + (size_t) (stream * cp.cps) * VDL2_MM_DT_ENTRIES + 4 * u + t);
+		}
 		mbar_wait(smem_u32(bars), phases & 1u);
 		phases ^= 1u;
 #pragma unroll 1
@@ -1145,18 +1167,36 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 					st = st1;
 				}
 			}
-			/* the windows are in registers: every channel of the stream takes its turn with its own weights */
+			/* the windows are in registers: every channel of the stream takes its turn with its own weights.  The weight
+			   fragments and per-dump constants come from L2: those of the NEXT (channel, dump pair) are requested before
+			   the current ones are used (the first profile of this kernel spent 10 cycles per issued instruction on them) */
 #pragma unroll 1
 			for (int c = 0; c < cp.cps; c++) {
 				const int ch = stream * cp.cps + c;
-				const uint4 *bt = cp.bt + (size_t) ch * VDL2_MM_BT_ENTRIES + btl;
-				const int4 *dt = cp.dt + (size_t) ch * VDL2_MM_DT_ENTRIES + dk0 * 4 + t;
+				uint4 Bc[2];
+				int4 dcc[2];
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					Bc[u] = Bn[u];
+					dcc[u] = dcn[u];
+				}
+				{	/* next iteration: channel c + 1 of this pair, or channel 0 of the next pair (clamped at the end of the row) */
+					const bool wrap = (c + 1 == cp.cps);
+					const int cn = wrap ? 0 : c + 1, dkn = wrap ? (dk0 + 2 < VDL2_DUMPS_PER_ROW ? dk0 + 2 : dk0) : dk0;
+					const uint4 *btn = cp.bt + (size_t) (stream * cp.cps + cn) * VDL2_MM_BT_ENTRIES + btl;
+					const int4 *dtn = cp.dt + (size_t) (stream * cp.cps + cn) * VDL2_MM_DT_ENTRIES + dkn * 4 + t;
+#pragma unroll
+					for (int u = 0; u < 2; u++) {
+						Bn[u] = __ldg(btn + ((sched[dkn + u] & 0x3f00u) >> 6));
+						dcn[u] = __ldg(dtn + 4 * u);
+					}
+				}
 				float2 o[2];
 #pragma unroll
 				for (int u = 0; u < 2; u++) {
 					const unsigned sk = skv[u];
-					uint4 B = __ldg(bt + ((sk & 0x3f00u) >> 6));	/* 6 p * 4 entries of 16 bytes */
-					const int4 dc = __ldg(dt + 4 * u);
+					uint4 B = Bc[u];	/* fragment of window phase 6 p * 4 entries of 16 bytes */
+					const int4 dc = dcc[u];
 					const int o16 = (int)((sk >> 16) & 127u), te = t32 - (int)(sk >> 23);
 					B.x &= shl_clamp(0xffffffffu, (uint32_t) max(o16 - t32, 0));
 					B.z &= shr_clamp(0xffffffffu, (uint32_t) max(te + 288, 0));
