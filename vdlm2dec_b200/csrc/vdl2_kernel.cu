@@ -608,7 +608,7 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	uint4 dn = ldg_keep(dp, l2keep);
 	mbar_wait(smem_u32(bars), phases & 1u);
 	phases ^= 1u;
-	static_assert(VDL2_DUMPS_PER_ROW % MM_UNROLL == 0 && (MM_NST & (MM_NST - 1)) == 0, "whole store groups per row; ring size a power of two");
+	static_assert(VDL2_DUMPS_PER_ROW % MM_UNROLL == 0 && MM_NST >= 4, "whole store groups per row; the phase-2 scratch needs four stages of room");
 #pragma unroll 1
 	for (int dk0 = 0; dk0 < VDL2_DUMPS_PER_ROW; dk0 += MM_UNROLL) {
 		/* software pipeline over the MM_UNROLL dumps of a store group: first every dump's window and weights go to registers
@@ -624,7 +624,7 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 			const unsigned sk = sched[dk0 + u];
 			dp += 4;
 			dn = ldg_keep(dp, l2keep);	/* the table carries one entry more than there are dumps */
-			const int st1 = (st + 1) & (MM_NST - 1);
+			const int st1 = (st + 1 == MM_NST) ? 0 : st + 1;
 			if (sk & VDL2_MM_W) {
 				mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
 				phases ^= 1u << st1;
@@ -1143,7 +1143,7 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 			for (int u = 0; u < 2; u++) {
 				const unsigned sk = sched[dk0 + u];
 				skv[u] = sk;
-				const int st1 = (st + 1) & (MM_NST - 1);
+				const int st1 = (st + 1 == MM_NST) ? 0 : st + 1;
 				if (sk & VDL2_MM_W) {
 					mbar_wait(smem_u32(bars + st1), (phases >> st1) & 1u);
 					phases ^= 1u << st1;
