@@ -149,3 +149,22 @@ def test_channeliser_one_pass_equals_fused_kernel_and_oracle(fmt):
             want = oracle(chn=chn, Fr=Fr, Fo=fo, taps=O_DUMPS).feed(iq[c // cps], fmt).dumps
             rms = np.sqrt(np.mean(np.abs(want) ** 2))
             assert np.abs(want - got[c, :rows * 84]).max() < 1e-5 * rms
+
+
+def test_create_failure_is_reported_and_leaks_nothing():
+    """vdl2_create() that fails half way (here: the staging buffer of an absurd max_samples does not fit the device) must
+    return the reason through vdl2_last_error(NULL) and tear the partial handle down: the next create succeeds and the
+    device's free memory is back where it was."""
+    import torch
+    from vdlm2dec_b200.api import Vdl2Error
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(3):
+        with pytest.raises(Vdl2Error) as ei:
+            Vdl2Gpu([(c, 136_975_000, -50_000) for c in range(64)], max_samples=1 << 36)
+        assert "failed" in str(ei.value) or "memory" in str(ei.value).lower()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"{(free0 - free1) >> 20} MiB still allocated after three failed creates"
+    g = Vdl2Gpu([(0, 136_975_000, -50_000)], max_samples=100_000)
+    g.process(np.full((1, 2 * 4000), 127, np.uint8))
+    assert g.stats()["samples_done"] == 4000
