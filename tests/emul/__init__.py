@@ -93,6 +93,13 @@ def build():
     return LIB
 
 
+def burst_pre_symbols(wrong: bool = False) -> int:
+    """Symbols whose phase the emulated warp computed ahead of the chain so far (BurstPre), on the true grid / on a wrong one."""
+    f = _lib.emul_burst_pre_symbols
+    f.restype = C.c_long
+    return int(f(1 if wrong else 0))
+
+
 def demod(dumps: np.ndarray, tile_dumps: int = 2688, chn: int = 0, Fr: int = 136_975_000, flags: int = 0, want_steps: bool = True):
     """Run the kernel's phase 2 source on the host over a decimated stream; returns (blocks, steps, syncs, syms)."""
     global _lib

@@ -44,6 +44,8 @@ struct TileJob {
 	vdl2::ChanRegs Rout[32];
 };
 static TileJob *g_job;
+static long g_bp_symbols[2];	/* symbols whose phase was computed ahead of the chain: on the right grid, on a wrong one */
+extern "C" long emul_burst_pre_symbols(int wrong) { return g_bp_symbols[wrong ? 1 : 0]; }
 
 static void lane_main(int lane)
 {
@@ -53,10 +55,33 @@ static void lane_main(int lane)
 	vdl2::IdlePre pre;
 	pre.valid = 0;
 	pre.used = 0;
+	vdl2::BurstPre bp;
+	bp.valid = 0;
 	if (j->pre_mode) {
 		/* the kernel runs the speculative stage BEFORE it has the previous tile's state: only a guess of (state, clk) */
 		const int cg = j->pre_mode == 1 ? R.clk : ((R.clk + 3) & 7);
 		const int sg = j->pre_mode == 1 ? R.state : VDL2_ST_WSYNC;
+		const long tix = (long)(j->dump_base / (j->nd > 0 ? j->nd : 1));
+		if (R.state == VDL2_ST_GETDATA && (j->pre_mode == 1 || (tix & 1))) {
+			/* a tile that starts inside a burst whose header is known: phases ahead (BurstPre), mode 1 on the true symbol grid and
+			   tap phase, mode 2 on a wrong one (must be ignored) */
+			const int c = R.clk;
+			const int k0 = (c >= 28) ? 1 : ((35 - c) >> 2);
+			const int r = c + 4 * k0 - 32, ds0 = k0 - 1;
+			if (r >= 0 && r < 4) {
+				const vdl2::BurstGeom g = vdl2::burst_geom(R.nbrow, R.nlbyte);
+				int last = ds0 + 8 * (g.nsym - R.symidx - 1);
+				last = last < j->nd - 1 ? last : j->nd - 1;
+				const int wrong = j->pre_mode == 2;
+				const int d0 = (ds0 + ((wrong && (tix & 2)) ? 3 : 0)) & 7;
+				const int rr = (wrong && !(tix & 2)) ? (r + 1) & 3 : r;
+				if (last >= 24) {
+					vdl2::burst_prephase(*j->kp, j->sd, j->S, bp, d0, last, rr, (wrong || !(tix & 4)) ? R.df : R.df + 1e-3f);
+					if (lane == 0)
+						g_bp_symbols[wrong] += (last - bp.d0) / 8 + 1;
+				}
+			}
+		} else
 		if (sg == VDL2_ST_WSYNC && cg >= 0 && cg < 8) {
 			vdl2::ChanRegs G;
 			memset(&G, 0, sizeof G);
@@ -64,7 +89,7 @@ static void lane_main(int lane)
 			G.state = VDL2_ST_WSYNC;
 			G.perr = 100.f;
 			int nph0 = 0;
-			vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, G, j->sd, j->S, j->hv, j->nd, j->dump_base, nph0, pre, true);
+			vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, G, j->sd, j->S, j->hv, j->nd, j->dump_base, nph0, pre, true, bp);
 		}
 		vw::sync();
 		if (lane < VDL2_HIST)
@@ -73,7 +98,7 @@ static void lane_main(int lane)
 		j->S.pht[lane + 32] = j->ph_hist[lane + 32];
 		vw::sync();
 	}
-	vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->S, j->hv, j->nd, j->dump_base, nph, pre, false);
+	vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, R, j->sd, j->S, j->hv, j->nd, j->dump_base, nph, pre, false, bp);
 	j->nph[lane] = nph;
 	j->Rout[lane] = R;
 	vw::g_done[lane] = 1;

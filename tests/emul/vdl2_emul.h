@@ -71,6 +71,7 @@ VQ float fmul(float a, float b) { return a * b; }
 template <class T> VQ T ldcg(const T * p) { return *p; }
 template <class T> VQ T ldg(const T * p) { return *p; }
 template <class T> VQ T *as_shared(T * p) { return p; }
+VQ unsigned f2bits(float a) { unsigned u; memcpy(&u, &a, 4); return u; }
 VQ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 VQ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 }

@@ -14,7 +14,7 @@ bursts = len(sys.argv) > 5 and sys.argv[5] == "bursts"
 x = torch.empty((nstreams, ns * 2), dtype=torch.uint8, device="cuda")
 if bursts:
     from vdlm2dec_b200.synth_torch import make_device_workload
-    x, fos_b, nb = make_device_workload(nstreams, ns, seed=1000, device=torch.device("cuda"))
+    x, fos_b, nb = make_device_workload(nstreams, ns, seed=1000, device=torch.device("cuda"), ch_per_stream=cps)
     print("bursts placed", nb)
 for s0 in range(0, 0 if bursts else nstreams, 64):  # gaussian-ish noise around 127, generated in slices to bound memory
     sl = x[s0:s0 + 64]
@@ -29,6 +29,7 @@ for r in range(reps):
     g.sync()
     st = g.stats()
     ms = st["last_kernel_ms"] or 1e-9
+    sp = st.get("spec") or ""
     print(f"rep {r}: {ms:.3f} ms  {nch*ns/ms/1e3:.1f} Msamples/s  {nstreams*ns*2/ms/1e6:.1f} GB/s  grid {st['grid']} smem {st['smem_bytes']}")
 print("blocks", len(g.drain_blocks()))
 if os.environ.get('VDL2_OVERLAP'):   # back-to-back launches, timed as a whole

@@ -55,7 +55,8 @@ struct Vdl2ChanState {
 	   of a burst gives its length; read without synchronisation (a wrong guess is detected, see idle_run) */
 	int64_t fc_dump;
 	int32_t fc_clk;
-	int32_t pad[3];
+	float fc_df;		/* frequency offset of the burst that ends at fc_dump (BurstPre) */
+	int32_t pad[2];
 };
 
 /* constant tables of the kernel (independent of rate and format, so handles can share them) */

@@ -92,6 +92,7 @@ VQ void sincos(float a, float &s, float &c) { sincosf(a, &s, &c); }
 VQ void sincos(float a, float &s, float &c) { s = __sinf(a); c = __cosf(a); }
 #endif
 VQ float rsqrt(float a) { return rsqrtf(a); }
+VQ unsigned f2bits(float a) { return __float_as_uint(a); }
 VQ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 VQ float fsub(float a, float b) { return __fsub_rn(a, b); }
 VQ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -589,6 +590,67 @@ struct IdlePre {
 	int used;		/* set by idle_run when the speculative results were accepted (statistics) */
 };
 
+/* One symbol: differential phase -> soft-table index -> soft bits (d8psk.c:209-216).  Returns both hard decisions every bit can
+   end in, because the descrambler (d8psk.c:54-65) either keeps the soft bit or replaces it by 1 - v before the comparison with
+   0.5: bit q = (v_q > 0.5), bit 3 + q = (1 - v_q > 0.5) (not complements of each other at v = 0.5, which the table contains). */
+VQ unsigned sym_decide(const Vdl2KParams & kp, float Pn, float Pp, float df, float &D, int &gi, float *v)
+{
+	D = vw::fsub(vw::fsub(Pn, Pp), df);
+	if (D >= VDL2_PI_F)
+		D = (float)((double)D - 2.0 * VDL2_PI_D);
+	if (D <= -VDL2_PI_F)
+		D = (float)((double)D + 2.0 * VDL2_PI_D);
+	gi = (int)roundf((float)(128.0 * (double)D / VDL2_PI_D + 128.0));	/* d8psk.c:213 */
+	gi = gi < 0 ? 0 : (gi > 256 ? 256 : gi);
+	unsigned ab = 0;
+#pragma unroll
+	for (int q = 0; q < 3; q++) {
+		/* per-lane index: from global memory (L1/L2), not the constant bank, which would serialise the 32
+		   distinct addresses of a symbol batch -- the largest stall of the burst path on the per-channel chain */
+		v[q] = kp.soft ? vw::ldg(kp.soft + q * 260 + gi) : c_tab.soft[q][gi];
+		ab |= (v[q] > 0.5f ? 1u : 0u) << q;
+		ab |= (vw::fsub(1.0f, v[q]) > 0.5f ? 1u : 0u) << (3 + q);
+	}
+	return ab;
+}
+
+/* Burst phases ahead of the chain.  Inside a burst nothing but the phase of the previous symbol is carried from one symbol
+   to the next (d8psk.c:314-332): the phase of the symbol at tile dump d is a function of the tile's own dumps and the tap
+   phase r alone as soon as its 17-dump window lies inside the tile (d >= 16).  Once a header is decoded the channel's forecast
+   says where the burst ends and with which r, so a tile that starts inside it computes those phases (the filter, its 17
+   strided L2 loads and the atan2: most of a symbol batch) while it waits for the previous tile; the burst loop then takes
+   them from bph[d >> 3] whenever the ACTUAL symbol grid and tap phase are the ones assumed -- never otherwise, so a stale or
+   torn forecast costs time, not correctness.  bph lives at the top of S.pht, which idle steps after the end of the burst
+   (at most (nd - d) / 2 of them) never reach while a precomputed symbol is still to be consumed. */
+struct BurstPre {
+	int valid, r, d0, dlast;	/* phases of the symbols at tile dumps d0, d0 + 8, ... <= dlast are in bph[d >> 3] */
+	float df;		/* and, for all but the first of them, the decisions (sym_decide) under this frequency offset in hb[d >> 3] */
+};
+#define VDL2_BPH_OFF (VDL2_PHT_LEN - VDL2_TILE_DUMPS / 8)
+
+VQ_RARE void burst_prephase(const Vdl2KParams & kp, const float2 * sd, const IdleScratch & S, BurstPre & bp, int d0, int dlast, int r, float df)
+{
+	float *bph = vw::as_shared(S.pht) + VDL2_BPH_OFF;
+	unsigned char *hb = reinterpret_cast < unsigned char *>(vw::as_shared(S.win));	/* the idle search's window buffer: idle here */
+	const int dmin = (d0 & 7) + 16;
+#pragma unroll 1
+	for (int d = dmin + 8 * vw::lane(); d <= dlast; d += 256)
+		bph[d >> 3] = filt_phase_any(sd, d, r);
+	vw::sync();
+#pragma unroll 1
+	for (int d = dmin + 8 + 8 * vw::lane(); d <= dlast; d += 256) {
+		float D, v[3];
+		int gi;
+		hb[d >> 3] = (unsigned char)sym_decide(kp, bph[d >> 3], bph[(d >> 3) - 1], df, D, gi, v);
+	}
+	bp.valid = dlast >= dmin;
+	bp.r = r;
+	bp.d0 = dmin;
+	bp.dlast = dlast;
+	bp.df = df;
+	vw::sync();
+}
+
 template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, ChanRegs & R, const float2 * sd, const IdleScratch & S, int nd,
 		 long long dump_base, int &pos, int &nph, IdlePre & pre, bool spec)
 {
@@ -734,7 +796,7 @@ template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, 
 }
 
 template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int chn, int Fr, ChanRegs & R, float2 * sd, const IdleScratch & S, float *hv,
-		   int nd, long long dump_base, int &nph, IdlePre & pre, bool spec)
+		   int nd, long long dump_base, int &nph, IdlePre & pre, bool spec, BurstPre & bp)
 {
 	const int lane = vw::lane();
 	int pos = 0;
@@ -743,6 +805,7 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 
 	while (pos < nd) {
 		if (R.state == VDL2_ST_WSYNC) {
+			bp.valid = 0;	/* idle steps write S.pht: whatever burst phases were computed ahead are gone */
 			idle_run < TAPS > (kp, ch, Fr, R, sd, S, nd, dump_base, pos, nph, pre, spec);
 		} else {
 			/* ---- burst: up to 32 symbols at dumps ds0, ds0+8, ... (d8psk.c:314-332) ---- */
@@ -767,33 +830,41 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 				nb = 1;	/* irregular clock (only after a non-finite timing estimate) */
 			const int d = ds0 + 8 * lane;
 			float Pn = 0.f;
-			if (lane < nb)
-				Pn = filt_phase_any(sd, d, r);
+			bool have6;	/* this lane's symbol was decided ahead of the chain (BurstPre) */
+			{
+				const bool grid_ok = bp.valid && r == bp.r && ((ds0 - bp.d0) & 7) == 0;
+				const bool have = grid_ok && d >= bp.d0 && d <= bp.dlast;
+				have6 = have && !head && d >= bp.d0 + 8 && vw::f2bits(R.df) == vw::f2bits(bp.df) && !(TAPS && (kp.taps & VDL2_TAP_SYMS_BIT));
+				if (have)
+					Pn = (vw::as_shared(S.pht) + VDL2_BPH_OFF)[d >> 3];
+				else if (lane < nb)
+					Pn = filt_phase_any(sd, d, r);
+				if (lane >= nb)
+					Pn = 0.f;
+			}
 			float Pp = vw::shfl_up(Pn, 1);
 			if (lane == 0)
 				Pp = R.P1;
-			float D = vw::fsub(vw::fsub(Pn, Pp), R.df);
-			if (D >= VDL2_PI_F)
-				D = (float)((double)D - 2.0 * VDL2_PI_D);
-			if (D <= -VDL2_PI_F)
-				D = (float)((double)D + 2.0 * VDL2_PI_D);
-			int gi = (int)roundf((float)(128.0 * (double)D / VDL2_PI_D + 128.0));	/* d8psk.c:213 */
-			gi = gi < 0 ? 0 : (gi > 256 ? 256 : gi);
-			if (lane >= nb)
-				gi = 128;
 			const int si = R.symidx + lane;
-			float v[3], V[3];
+			float D = 0.f, v[3] = { 0.f, 0.f, 0.f };
+			int gi = 128;
+			unsigned ab;
+			if (have6)
+				ab = (reinterpret_cast < const unsigned char *>(vw::as_shared(S.win)))[d >> 3];
+			else
+				ab = sym_decide(kp, Pn, Pp, R.df, D, gi, v);
+			/* descrambler, d8psk.c:54-65: bits 3 si .. 3 si + 2 of the sequence */
+			const int b0 = 3 * si;
+			const unsigned w0 = kp.soft ? vw::ldg(kp.scr + ((b0 >> 5) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[(b0 >> 5) & (VDL2_SCR_WORDS - 1)];
+			const unsigned w1 = kp.soft ? vw::ldg(kp.scr + (((b0 >> 5) + 1) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[((b0 >> 5) + 1) & (VDL2_SCR_WORDS - 1)];
+			const unsigned s3 = (unsigned)((((unsigned long long)w1 << 32) | w0) >> (b0 & 31)) & 7u;
+			float V[3];
 			unsigned hard = 0;
 #pragma unroll
 			for (int q = 0; q < 3; q++) {
-				/* per-lane index: from global memory (L1/L2), not the constant bank, which would serialise the 32
-				   distinct addresses of a symbol batch -- the largest stall of the burst path on the per-channel chain */
-				v[q] = kp.soft ? vw::ldg(kp.soft + q * 260 + gi) : c_tab.soft[q][gi];
-				const int b = 3 * si + q;
-				const unsigned sw_ = kp.soft ? vw::ldg(kp.scr + ((b >> 5) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[(b >> 5) & (VDL2_SCR_WORDS - 1)];
-				const unsigned sb = (sw_ >> (b & 31)) & 1u;
-				V[q] = sb ? vw::fsub(1.0f, v[q]) : v[q];	/* descrambler, d8psk.c:54-65 */
-				hard |= (V[q] > 0.5f ? 1u : 0u) << q;
+				const unsigned sb = (s3 >> q) & 1u;
+				V[q] = sb ? vw::fsub(1.0f, v[q]) : v[q];
+				hard |= ((ab >> (sb ? 3 + q : q)) & 1u) << q;
 			}
 			const float Plast = vw::shfl(Pn, nb - 1);
 
@@ -849,54 +920,30 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 					if (kp.state && lane == 0) {	/* forecast for the tiles after this burst (Vdl2ChanState.fc_*) */
 						kp.state[ch].fc_dump = idle_from;
 						kp.state[ch].fc_clk = r;
+						kp.state[ch].fc_df = R.df;
 					}
 				}
 			} else {
 				/* payload: pack 3 bits per lane into bytes, LSB first (d8psk.c:117-206) */
-				const unsigned m0 = vw::ballot(hard & 1u), m1 = vw::ballot(hard & 2u), m2 = vw::ballot(hard & 4u);
+				/* the bit stream of the batch = the R.nbitacc bits left over + 3 bits per lane; byte number `lane` of it starts at
+				   symbol bit sp and takes its 8 bits from at most 4 consecutive symbols */
 				const int nbits = R.nbitacc + 3 * nb;
 				const int total = g.nd + g.nf;
 				int nbytes = nbits >> 3;
 				if (R.bytes_done + nbytes > total)
 					nbytes = total - R.bytes_done;
-				if (lane < nbytes) {
-					unsigned byte = 0;
-#pragma unroll
-					for (int i = 0; i < 8; i++) {
-						const int p = 8 * lane + i;
-						unsigned bit;
-						if (p < R.nbitacc) {
-							bit = ((unsigned)R.bitacc >> p) & 1u;
-						} else {
-							const int p2 = p - R.nbitacc;
-							const int j = (p2 * 43691) >> 17;	/* p2 / 3 */
-							const int q = p2 - 3 * j;
-							const unsigned mm = q == 0 ? m0 : (q == 1 ? m1 : m2);
-							bit = (mm >> j) & 1u;
-						}
-						byte |= bit << i;
-					}
+				const int sp = 8 * lane - R.nbitacc;
+				const int j0 = sp > 0 ? (sp * 43691) >> 17 : 0;	/* sp / 3 */
+				const unsigned h4 = vw::shfl(hard, j0 & 31) | (vw::shfl(hard, (j0 + 1) & 31) << 3) | (vw::shfl(hard, (j0 + 2) & 31) << 6)
+				    | (vw::shfl(hard, (j0 + 3) & 31) << 9);
+				const unsigned byte = (sp >= 0 ? (h4 >> (sp - 3 * j0)) : ((unsigned)R.bitacc | (h4 << (-sp)))) & 0xffu;
+				if (lane < nbytes)
 					curblk[byte_slot(g, R.bytes_done + lane)] = (unsigned char)byte;
-				}
-				/* bits left over for the next batch */
+				/* bits left over for the next batch: the head of the byte that would come next */
 				int left = nbits - 8 * nbytes;
-				unsigned acc = 0;
 				if (left > 7)
 					left = 0;	/* only at the end of the burst: discarded (d8psk.c:203) */
-				for (int i = 0; i < left; i++) {
-					const int p = 8 * nbytes + i;
-					unsigned bit;
-					if (p < R.nbitacc) {
-						bit = ((unsigned)R.bitacc >> p) & 1u;
-					} else {
-						const int p2 = p - R.nbitacc;
-						const int j = p2 / 3;
-						const int q = p2 - 3 * j;
-						const unsigned mm = q == 0 ? m0 : (q == 1 ? m1 : m2);
-						bit = (mm >> j) & 1u;
-					}
-					acc |= bit << i;
-				}
+				const unsigned acc = vw::shfl(byte, nbytes & 31) & ((1u << left) - 1u);
 				R.bitacc = (int)acc;
 				R.nbitacc = left;
 				R.bytes_done += nbytes;

@@ -551,8 +551,8 @@ static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_p
 		CK(h, cudaMemcpy(h->d_dcorr, dc.data(), sizeof(float4) * dc.size(), cudaMemcpyHostToDevice));
 	}
 
-	CK(h, cudaMalloc(&h->d_ticket, 64));
-	CK(h, cudaMemset(h->d_ticket, 0, 64));
+	CK(h, cudaMalloc(&h->d_ticket, 256));	/* words 16..: chain statistics of a -DVDL2_CHAIN_STATS build */
+	CK(h, cudaMemset(h->d_ticket, 0, 256));
 	h->d_outq_count = h->d_ticket + 4;
 	h->d_dropped = h->d_ticket + 8;
 	CK(h, cudaMalloc(&h->d_progress, sizeof(int) * nch));
@@ -768,6 +768,17 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 		cudaMemcpy(c, h->d_ticket + 12, sizeof c, cudaMemcpyDeviceToHost);
 		fprintf(stderr, "vdl2gpu: prepass used %u wasted %u idle-without %u burst-start %u\n", c[0], c[1], c[2], c[3]);
 		cudaMemset(h->d_ticket + 12, 0, sizeof c);
+		unsigned cs[28];
+		cudaMemcpy(cs, h->d_ticket + 16, sizeof cs, cudaMemcpyDeviceToHost);
+		static const char *kinds[7] = { "idle, speculation used", "idle, pass A on the chain", "idle -> trigger -> in burst", "idle -> whole burst -> idle",
+			"in burst -> in burst", "in burst -> idle", "in burst -> idle -> next trigger" };
+		for (int k = 0; k < 7; k++)
+			if (cs[4 * k]) {
+				unsigned long long ns;
+				memcpy(&ns, cs + 4 * k + 2, 8);
+				fprintf(stderr, "vdl2gpu: chain %-32s %7u tiles  %8.2f us each  %10.1f us total\n", kinds[k], cs[4 * k], ns * 1e-3 / cs[4 * k], ns * 1e-3);
+			}
+		cudaMemset(h->d_ticket + 16, 0, sizeof cs);
 	}
 
 	const long long items = (long long)kp.ntiles * kp.nch;

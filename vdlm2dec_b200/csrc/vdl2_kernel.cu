@@ -108,6 +108,38 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 	return *reinterpret_cast < float2 * >(&rd);
 }
 
+#ifndef VDL2_MAX_RESPEC
+#define VDL2_MAX_RESPEC 8	/* repeats of the speculative stage per tile (one per burst header decoded while it waits) */
+#endif
+#ifndef VDL2_SPEC_AHEAD
+#define VDL2_SPEC_AHEAD 12	/* tiles: how far behind the start of a tile the forecast point may lie for the tile to speculate on it */
+#endif
+/* What a tile starting at dump_base can do ahead of its turn in the channel's chain, from the forecast
+   (Vdl2ChanState.fc_dump / fc_clk: the end of the last idle tile, or of the burst whose header was decoded last):
+     0..7   the channel is idle there: the tick clock the tile begins with (speculative pass A, see IdlePre);
+     8..39  the tile starts inside that burst: 8 + 4 * (first symbol dump mod 8) + tap phase (burst phases ahead, see BurstPre);
+     -1     nothing.
+   Two unsynchronised words: a torn pair gives a wrong key, and the demodulator verifies whatever was precomputed under it. */
+static __device__ __forceinline__ int forecast_key(const Vdl2ChanState * gs, long long dump_base, int nd, int &bd0, int &bdlast, float &bdf)
+{
+	const long long F = *(const volatile long long *)&gs->fc_dump;
+	const int c = *(const volatile int *)&gs->fc_clk & 7;
+	if (F > dump_base) {	/* the last symbol of the burst is at dump F - 1, one symbol every 8 dumps */
+		const long long rel = F - 1 - dump_base;
+		if (c >= 4 || rel < 24)
+			return -1;
+		bd0 = (int)(rel & 7);
+		bdlast = rel < (long long)nd ? (int)rel : nd - 1;
+		bdf = *(const volatile float *)&gs->fc_df;
+		return 8 + 4 * bd0 + c;
+	}
+	if (dump_base - F > (long long)VDL2_SPEC_AHEAD * VDL2_TILE_DUMPS)
+		return -1;	/* too far ahead of the chain to be worth a guess: every burst in between would void it (the tile asks again while it waits) */
+	const int s = (c >= 4) ? 0 : 1;	/* dump F + s is the first idle step; then every 2nd dump */
+	const long long e = dump_base - F - s;
+	return (c & 3) + ((e >= 0 && (e & 1LL) == 0) ? 4 : 0);
+}
+
 /* ------------------------------------------------------------------ phase 1: channeliser */
 struct MixAcc {			/* partial sums of one dump; .x/.y = even/odd sample of a pair (8-bit formats) */
 	float2 A, B, C, G;	/* A: xr*wr  B: xi*wi  C: xr*wi  G: xi*wr   (cf32: A = (I,Q)*re, C = (I,Q)*im) */
@@ -935,32 +967,66 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		ChanRegs R;
 		unsigned n_dumps = 0;
 		int chn = 0, Fr = 0, nph = 0, had_pre = 0, idle_at_start = 0;
+#ifdef VDL2_CHAIN_STATS
+		unsigned long long cs_t0 = 0, cs_t1 = 0;
+		long long cs_sync0 = 0;
+#endif
+		int guess = -1, nrespec = 0;	/* what the speculative stage assumed (forecast_key; -1: nothing), times it was repeated */
+		BurstPre bp;
+		bp.valid = 0;
 		const long long dump_base = kp.dump_base + (long long)row0 * VDL2_DUMPS_PER_ROW;
+		const bool can_spec = !(TAPS && ((kp.taps & VDL2_TAP_STEPS_BIT) || (kp.flags & (VDL2_FLAG_NO_SCREEN | VDL2_FLAG_NO_PREPASS))));
 #pragma unroll 1
 		for (int stage = 0; stage < 2; stage++) {
 			const bool spec = (stage == 0);
 			if (spec) {
-				if (TAPS && ((kp.taps & VDL2_TAP_STEPS_BIT) || (kp.flags & (VDL2_FLAG_NO_SCREEN | VDL2_FLAG_NO_PREPASS))))
+				if (!can_spec)
 					continue;
 				/* the channel's forecast (Vdl2ChanState.fc_*), read without synchronisation: idle_run verifies the guess */
-				const long long F = __ldcg(&gs->fc_dump);
-				const int c = __ldcg(&gs->fc_clk) & 7;
-				if (F > dump_base)
-					continue;	/* as far as is known the tile starts inside a burst */
-				const int s = (c >= 4) ? 0 : 1;	/* dump F + s is the first idle step; then every 2nd dump */
-				const long long e = dump_base - F - s;
+				int bd0 = 0, bdlast = 0;
+				float bdf = 0.f;
+				bp.valid = 0;
+				guess = forecast_key(gs, dump_base, nd, bd0, bdlast, bdf);
+				if (guess < 0)
+					continue;
+				if (guess >= 8) {	/* as far as is known the tile starts inside a burst */
+					vdl2::burst_prephase(kp, sd, scr, bp, bd0, bdlast, guess & 3, bdf);
+					continue;
+				}
 				memset(&R, 0, sizeof R);
-				R.clk = (c & 3) + ((e >= 0 && (e & 1LL) == 0) ? 4 : 0);
+				R.clk = guess;
 				R.state = VDL2_ST_WSYNC;
 				R.perr = 100.f;
 			} else {
-				/* wait for the previous tile of this channel, load its state */
+				/* wait for the previous tile of this channel, load its state.  While waiting, watch the forecast: a burst
+				   header decoded further up the chain changes the tick clock every later tile will start with, and a
+				   tile that speculated on the old one (with few channels EVERY later tile of the launch has: they all
+				   start at once) would otherwise repeat pass A inside the chain, one tile after the other */
+				int redo = 0;
 				if (lane == 0) {
 					const volatile int *pr = kp.progress + ch;
-					while ((int)((unsigned)(kp.tile_base + tile) - (unsigned)*pr) > 0)	/* tiles completed since create (wrap-safe): launches may overlap */
+					while ((int)((unsigned)(kp.tile_base + tile) - (unsigned)*pr) > 0) {	/* tiles completed since create (wrap-safe): launches may overlap */
+						if (can_spec && nrespec < VDL2_MAX_RESPEC) {
+							int t0, t1;
+							float t2;
+							const int g2 = forecast_key(gs, dump_base, nd, t0, t1, t2);
+							if (g2 >= 0 && g2 != guess) {
+								redo = 1;
+								break;
+							}
+						}
 						__nanosleep(200);
+					}
 				}
-				__syncwarp();
+#ifdef VDL2_CHAIN_STATS
+				asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_t0));
+#endif
+				redo = __shfl_sync(0xffffffffu, redo, 0);
+				if (redo) {
+					nrespec++;
+					stage = -1;
+					continue;
+				}
 				__threadfence();
 				if (lane < VDL2_HIST)
 					__stcg(sd + lane, make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane)));
@@ -1000,9 +1066,12 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				}
 				had_pre = pre.valid;
 				idle_at_start = (R.state == VDL2_ST_WSYNC);
+#ifdef VDL2_CHAIN_STATS
+				cs_sync0 = R.sync_dump;
+#endif
 			}
 			nph = 0;
-			demod_tile < TAPS > (kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph, pre, spec);
+			demod_tile < TAPS > (kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph, pre, spec, bp);
 			__syncwarp();
 		}
 #ifndef VDL2_NO_STATS
@@ -1047,6 +1116,15 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		}
 		__threadfence();
 		__syncwarp();
+#ifdef VDL2_CHAIN_STATS	/* debug build: time on the chain (previous tile ready -> this tile published) by kind of tile, ticket[16 + 4 * kind] */
+		if (lane == 0) {
+			asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_t1));
+			const bool idle_end = R.state == VDL2_ST_WSYNC, trig = R.sync_dump != cs_sync0;
+			const int kind = idle_at_start ? (trig ? (idle_end ? 3 : 2) : (pre.used ? 0 : 1)) : (idle_end ? (trig ? 6 : 5) : 4);
+			atomicAdd(kp.ticket + 16 + 4 * kind, 1u);
+			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 16 + 4 * kind + 2), cs_t1 - cs_t0);
+		}
+#endif
 		if (lane == 0)
 			atomicExch(kp.progress + ch, kp.tile_base + tile + 1);
 		__syncwarp();
