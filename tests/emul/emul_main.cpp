@@ -55,6 +55,7 @@ static void lane_main(int lane)
 	vdl2::IdlePre pre;
 	pre.valid = 0;
 	pre.used = 0;
+	pre.pos0 = 0;
 	vdl2::BurstPre bp;
 	bp.valid = 0;
 	if (j->pre_mode) {
@@ -70,8 +71,8 @@ static void lane_main(int lane)
 			const int r = c + 4 * k0 - 32, ds0 = k0 - 1;
 			if (r >= 0 && r < 4) {
 				const vdl2::BurstGeom g = vdl2::burst_geom(R.nbrow, R.nlbyte);
-				int last = ds0 + 8 * (g.nsym - R.symidx - 1);
-				last = last < j->nd - 1 ? last : j->nd - 1;
+				const int end = ds0 + 8 * (g.nsym - R.symidx - 1);	/* tile dump of the last symbol of the burst */
+				const int last = end < j->nd - 1 ? end : j->nd - 1;
 				const int wrong = j->pre_mode == 2;
 				const int d0 = (ds0 + ((wrong && (tix & 2)) ? 3 : 0)) & 7;
 				const int rr = (wrong && !(tix & 2)) ? (r + 1) & 3 : r;
@@ -79,6 +80,20 @@ static void lane_main(int lane)
 					vdl2::burst_prephase(*j->kp, j->sd, j->S, bp, d0, last, rr, (wrong || !(tix & 4)) ? R.df : R.df + 1e-3f);
 					if (lane == 0)
 						g_bp_symbols[wrong] += (last - bp.d0) / 8 + 1;
+				}
+				if (end < j->nd - 1 && !(wrong && (tix & 2))) {
+					/* the burst ends inside the tile: speculative idle search of the rest (IdlePre.pos0), with the right tick clock or,
+					   in mode 2, a wrong one */
+					vdl2::ChanRegs G;
+					memset(&G, 0, sizeof G);
+					G.clk = wrong ? (r + 2) & 3 : r;
+					G.state = VDL2_ST_WSYNC;
+					G.perr = 100.f;
+					int nph0 = 0;
+					pre.pos0 = end + 1;
+					vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, G, j->sd, j->S, j->hv, j->nd, j->dump_base, nph0, pre, true, bp);
+					if (lane == 0 && pre.valid)
+						g_bp_symbols[wrong] += 1000000;
 				}
 			}
 		} else
@@ -89,6 +104,7 @@ static void lane_main(int lane)
 			G.state = VDL2_ST_WSYNC;
 			G.perr = 100.f;
 			int nph0 = 0;
+			pre.pos0 = 0;
 			vdl2::demod_tile < true > (*j->kp, j->ch, j->chn, j->Fr, G, j->sd, j->S, j->hv, j->nd, j->dump_base, nph0, pre, true, bp);
 		}
 		vw::sync();
@@ -198,6 +214,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	std::vector < float2 > vwin(96);
 	std::vector < unsigned short >cand(VDL2_CAND_CAP + VDL2_CAND0_CAP);
 	std::vector < float2 > win(VDL2_WIN_LEN);
+	std::vector < unsigned char >hbuf(VDL2_TILE_DUMPS / 8);
 	for (int i = 0; i < VDL2_HIST; i++)
 		sd[i] = make_float2(0.f, 0.f);
 	vdl2::ChanRegs R;
@@ -233,6 +250,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 			}
 		}
 		job.S.win = win.data();
+		job.S.hb = hbuf.data();
 		job.hv = hv;
 		job.R0 = R;
 		run_warp(&job);

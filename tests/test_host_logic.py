@@ -80,7 +80,10 @@ def test_phase2_speculative_pass_a(tile, mode):
     b1, _, sy1, sm1 = emul.demod(o.dumps, tile, flags=mode, want_steps=False)
     # tiles that start inside a burst whose header is known also take the burst phases ahead of the chain (BurstPre): on the true
     # symbol grid (0x100) they are consumed, on a wrong grid or tap phase (0x200) they must be ignored
-    assert emul.burst_pre_symbols(mode == 0x200) - n_pre > 100
+    n_now = emul.burst_pre_symbols(mode == 0x200) - n_pre
+    assert n_now % 1_000_000 > 100
+    # ... and where the burst ends inside the tile, the idle search of the rest of it ran ahead of the chain as well (IdlePre.pos0)
+    assert n_now // 1_000_000 >= 1 or mode == 0x200   # (with the wrong guess only on some tiles: may not occur)
     assert len(b0) == len(b1) and np.array_equal(b0["data"], b1["data"]) and np.array_equal(b0["sync_dump"], b1["sync_dump"])
     assert sy0.tobytes() == sy1.tobytes() and sm0.tobytes() == sm1.tobytes()
     compare_channel(o, b1, sy1, sm1, None, None)

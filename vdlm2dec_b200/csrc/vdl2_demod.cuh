@@ -390,6 +390,7 @@ struct IdleScratch {
 	unsigned short *cand;	/* [VDL2_CAND_CAP]: steps that passed the screen */
 	unsigned short *cand0;	/* [VDL2_CAND0_CAP]: same for the head of a speculatively screened tile (idle_prepass) */
 	float2 *win;		/* [VDL2_WIN_LEN]: the dumps one batch of 32 steps filters (copied from the L2-resident stream) */
+	unsigned char *hb;	/* [VDL2_TILE_DUMPS / 8]: decisions of burst symbols taken ahead of the chain (BurstPre) */
 };
 
 /* filter only (no phase): 17 taps, steady-state tap phase */
@@ -585,6 +586,7 @@ VQ_PASSA int idle_passA(const float2 * sd, IdleScratch S, float *ph, int r, int 
    loop of phase 2, exists once in the kernel (out of line it ran 8 % slower, twice inline it does not fit
    the instruction cache). */
 struct IdlePre {
+	int pos0;		/* tile dump the speculative run starts at: 0, or the dump after the last symbol of a burst that ends inside the tile */
 	int valid, clk, ncand;
 	bool overflow;
 	int used;		/* set by idle_run when the speculative results were accepted (statistics) */
@@ -620,28 +622,29 @@ VQ unsigned sym_decide(const Vdl2KParams & kp, float Pn, float Pp, float df, flo
    says where the burst ends and with which r, so a tile that starts inside it computes those phases (the filter, its 17
    strided L2 loads and the atan2: most of a symbol batch) while it waits for the previous tile; the burst loop then takes
    them from bph[d >> 3] whenever the ACTUAL symbol grid and tap phase are the ones assumed -- never otherwise, so a stale or
-   torn forecast costs time, not correctness.  bph lives at the top of S.pht, which idle steps after the end of the burst
-   (at most (nd - d) / 2 of them) never reach while a precomputed symbol is still to be consumed. */
+   torn forecast costs time, not correctness.  The phases live at the top of S.pht, filled downwards (VDL2_BPH): the phases of
+   the idle steps after the end of a burst at dump d -- the speculative pass A of the rest of the tile runs ahead of the chain
+   too -- end below index 1408 - d / 2, the burst's above 1439 - d / 8. */
 struct BurstPre {
 	int valid, r, d0, dlast;	/* phases of the symbols at tile dumps d0, d0 + 8, ... <= dlast are in bph[d >> 3] */
 	float df;		/* and, for all but the first of them, the decisions (sym_decide) under this frequency offset in hb[d >> 3] */
 };
-#define VDL2_BPH_OFF (VDL2_PHT_LEN - VDL2_TILE_DUMPS / 8)
+#define VDL2_BPH(d) (VDL2_PHT_LEN - 1 - ((d) >> 3))
 
 VQ_RARE void burst_prephase(const Vdl2KParams & kp, const float2 * sd, const IdleScratch & S, BurstPre & bp, int d0, int dlast, int r, float df)
 {
-	float *bph = vw::as_shared(S.pht) + VDL2_BPH_OFF;
-	unsigned char *hb = reinterpret_cast < unsigned char *>(vw::as_shared(S.win));	/* the idle search's window buffer: idle here */
+	float *pht = vw::as_shared(S.pht);
+	unsigned char *hb = vw::as_shared(S.hb);
 	const int dmin = (d0 & 7) + 16;
 #pragma unroll 1
 	for (int d = dmin + 8 * vw::lane(); d <= dlast; d += 256)
-		bph[d >> 3] = filt_phase_any(sd, d, r);
+		pht[VDL2_BPH(d)] = filt_phase_any(sd, d, r);
 	vw::sync();
 #pragma unroll 1
 	for (int d = dmin + 8 + 8 * vw::lane(); d <= dlast; d += 256) {
 		float D, v[3];
 		int gi;
-		hb[d >> 3] = (unsigned char)sym_decide(kp, bph[d >> 3], bph[(d >> 3) - 1], df, D, gi, v);
+		hb[d >> 3] = (unsigned char)sym_decide(kp, pht[VDL2_BPH(d)], pht[VDL2_BPH(d - 8)], df, D, gi, v);
 	}
 	bp.valid = dlast >= dmin;
 	bp.r = r;
@@ -660,7 +663,7 @@ template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, 
 	const int c4 = R.clk >= 4;
 	const int p0 = pos + (c4 ? 0 : 1);	/* dump of the first step: a step every 2nd dump (d8psk.c:248-250) */
 	const int r = c4 ? R.clk - 4 : R.clk;	/* tap phase of every step of the run */
-	const bool use_pre = !spec && pre.valid && pos == 0 && nph == 0 && pre.clk == R.clk && R.perr >= 4.0f
+	const bool use_pre = !spec && pre.valid && pos == pre.pos0 && nph == 0 && pre.clk == R.clk && R.perr >= 4.0f
 	    && !(TAPS && (kp.taps & VDL2_TAP_STEPS_BIT)) && !(TAPS && (kp.flags & VDL2_FLAG_NO_SCREEN));
 	pre.valid = 0;		/* a prepass covers the first run of the tile only */
 	if (use_pre)
@@ -799,13 +802,14 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 		   int nd, long long dump_base, int &nph, IdlePre & pre, bool spec, BurstPre & bp)
 {
 	const int lane = vw::lane();
-	int pos = 0;
+	int pos = spec ? pre.pos0 : 0;
 	nph = 0;
 	unsigned char *curblk = kp.curblk + (size_t) ch * 2048;
 
 	while (pos < nd) {
 		if (R.state == VDL2_ST_WSYNC) {
-			bp.valid = 0;	/* idle steps write S.pht: whatever burst phases were computed ahead are gone */
+			if (!spec)
+				bp.valid = 0;	/* idle steps write S.pht: whatever burst phases were computed ahead are gone */
 			idle_run < TAPS > (kp, ch, Fr, R, sd, S, nd, dump_base, pos, nph, pre, spec);
 		} else {
 			/* ---- burst: up to 32 symbols at dumps ds0, ds0+8, ... (d8psk.c:314-332) ---- */
@@ -836,7 +840,7 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 				const bool have = grid_ok && d >= bp.d0 && d <= bp.dlast;
 				have6 = have && !head && d >= bp.d0 + 8 && vw::f2bits(R.df) == vw::f2bits(bp.df) && !(TAPS && (kp.taps & VDL2_TAP_SYMS_BIT));
 				if (have)
-					Pn = (vw::as_shared(S.pht) + VDL2_BPH_OFF)[d >> 3];
+					Pn = vw::as_shared(S.pht)[VDL2_BPH(d)];
 				else if (lane < nb)
 					Pn = filt_phase_any(sd, d, r);
 				if (lane >= nb)
@@ -850,7 +854,7 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 			int gi = 128;
 			unsigned ab;
 			if (have6)
-				ab = (reinterpret_cast < const unsigned char *>(vw::as_shared(S.win)))[d >> 3];
+				ab = vw::as_shared(S.hb)[d >> 3];
 			else
 				ab = sym_decide(kp, Pn, Pp, R.df, D, gi, v);
 			/* descrambler, d8psk.c:54-65: bits 3 si .. 3 si + 2 of the sequence */

@@ -778,6 +778,13 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 				memcpy(&ns, cs + 4 * k + 2, 8);
 				fprintf(stderr, "vdl2gpu: chain %-32s %7u tiles  %8.2f us each  %10.1f us total\n", kinds[k], cs[4 * k], ns * 1e-3 / cs[4 * k], ns * 1e-3);
 			}
+		if (cs[0]) {
+			unsigned long long part[3];
+			cudaMemcpy(part, h->d_ticket + 48, sizeof part, cudaMemcpyDeviceToHost);
+			fprintf(stderr, "vdl2gpu: chain idle step = load %.2f + demodulate %.2f + store/fence %.2f us\n", part[0] * 1e-3 / cs[0], part[1] * 1e-3 / cs[0],
+				part[2] * 1e-3 / cs[0]);
+			cudaMemset(h->d_ticket + 48, 0, sizeof part);
+		}
 		cudaMemset(h->d_ticket + 16, 0, sizeof cs);
 	}
 

@@ -111,6 +111,9 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 #ifndef VDL2_MAX_RESPEC
 #define VDL2_MAX_RESPEC 8	/* repeats of the speculative stage per tile (one per burst header decoded while it waits) */
 #endif
+#ifndef VDL2_CHAIN_POLL_NS
+#define VDL2_CHAIN_POLL_NS 100	/* back-off of the wait for the previous tile of the channel */
+#endif
 #ifndef VDL2_SPEC_AHEAD
 #define VDL2_SPEC_AHEAD 12	/* tiles: how far behind the start of a tile the forecast point may lie for the tile to speculate on it */
 #endif
@@ -796,7 +799,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	scr.win = reinterpret_cast < float2 * >(stage0 + VDL2_PHT_LEN * 4 + 96 * 8);
 	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8);
 	scr.cand0 = scr.cand + VDL2_CAND_CAP;
-	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + (VDL2_CAND_CAP + VDL2_CAND0_CAP) * 2 <= STAGES_BYTES,
+	scr.hb = reinterpret_cast < unsigned char *>(scr.cand0 + VDL2_CAND0_CAP);
+	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + (VDL2_CAND_CAP + VDL2_CAND0_CAP) * 2 + VDL2_TILE_DUMPS / 8 <= STAGES_BYTES,
 		      "phase 2 scratch must fit the stages");
 	static_assert(NBAR <= 8, "mbarriers live in 64 bytes");
 
@@ -961,6 +965,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		     chain of phase 2 executions is the critical path of the launch;
 		   stage 1: wait for the previous tile, load its state, demodulate. ---- */
 		Vdl2ChanState *gs = kp.state + ch;
+		/* last 16 dumps of the tile, the next tile's filter history: fetched now, not on the chain (an L2 round trip) */
+		const float2 htail = __ldcg(sd + nd + (lane & (VDL2_HIST - 1)));
 		IdlePre pre;
 		pre.valid = 0;
 		pre.used = 0;
@@ -968,7 +974,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 		unsigned n_dumps = 0;
 		int chn = 0, Fr = 0, nph = 0, had_pre = 0, idle_at_start = 0;
 #ifdef VDL2_CHAIN_STATS
-		unsigned long long cs_t0 = 0, cs_t1 = 0;
+		unsigned long long cs_t0 = 0, cs_t1 = 0, cs_ta = 0, cs_tb = 0;
 		long long cs_sync0 = 0;
 #endif
 		int guess = -1, nrespec = 0;	/* what the speculative stage assumed (forecast_key; -1: nothing), times it was repeated */
@@ -985,16 +991,22 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				/* the channel's forecast (Vdl2ChanState.fc_*), read without synchronisation: idle_run verifies the guess */
 				int bd0 = 0, bdlast = 0;
 				float bdf = 0.f;
+				/* whatever an earlier pass of this stage left is void: both kinds of results share S.pht */
 				bp.valid = 0;
+				pre.valid = 0;
+				pre.pos0 = 0;
 				guess = forecast_key(gs, dump_base, nd, bd0, bdlast, bdf);
 				if (guess < 0)
 					continue;
 				if (guess >= 8) {	/* as far as is known the tile starts inside a burst */
 					vdl2::burst_prephase(kp, sd, scr, bp, bd0, bdlast, guess & 3, bdf);
-					continue;
+					if (bdlast >= nd - 1)
+						continue;
+					/* ... that ends inside it, at dump bdlast: the idle search of the rest of the tile, ahead of the chain as well */
+					pre.pos0 = bdlast + 1;
 				}
 				memset(&R, 0, sizeof R);
-				R.clk = guess;
+				R.clk = guess >= 8 ? (guess & 3) : guess;
 				R.state = VDL2_ST_WSYNC;
 				R.perr = 100.f;
 			} else {
@@ -1015,8 +1027,13 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 								break;
 							}
 						}
-						__nanosleep(200);
+						__nanosleep(VDL2_CHAIN_POLL_NS);
 					}
+#ifndef VDL2_CHAIN_FENCE_SC
+					/* acquire side of the hand-over: one fence in the polling lane, the warp shuffle below extends it to the others
+					   (a sequentially consistent fence in every lane, __threadfence(), costs a microsecond per tile of the chain) */
+					asm volatile ("fence.acq_rel.gpu;":::"memory");
+#endif
 				}
 #ifdef VDL2_CHAIN_STATS
 				asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_t0));
@@ -1027,7 +1044,9 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 					stage = -1;
 					continue;
 				}
+#ifdef VDL2_CHAIN_FENCE_SC	/* A/B */
 				__threadfence();
+#endif
 				if (lane < VDL2_HIST)
 					__stcg(sd + lane, make_float2(__ldcg(gs->hist_re + lane), __ldcg(gs->hist_im + lane)));
 				scr.pht[lane] = __ldcg(gs->ph + lane);
@@ -1068,11 +1087,15 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				idle_at_start = (R.state == VDL2_ST_WSYNC);
 #ifdef VDL2_CHAIN_STATS
 				cs_sync0 = R.sync_dump;
+				asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_ta));
 #endif
 			}
 			nph = 0;
 			demod_tile < TAPS > (kp, ch, chn, Fr, R, sd, scr, hv, nd, dump_base, nph, pre, spec, bp);
 			__syncwarp();
+#ifdef VDL2_CHAIN_STATS
+			asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_tb));
+#endif
 		}
 #ifndef VDL2_NO_STATS
 		if (lane == 0)	/* statistics: 0 speculation used, 1 wasted, 2 idle tile without one, 3 tile that starts inside a burst */
@@ -1081,9 +1104,8 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
 		/* ---- store state, release the channel ---- */
 		if (lane < VDL2_HIST) {
-			const float2 h = __ldcg(sd + nd + lane);	/* last 16 dumps of the tile */
-			gs->hist_re[lane] = h.x;
-			gs->hist_im[lane] = h.y;
+			gs->hist_re[lane] = htail.x;
+			gs->hist_im[lane] = htail.y;
 		}
 		gs->ph[lane] = scr.pht[nph + lane];
 		gs->ph[lane + 32] = scr.pht[nph + lane + 32];
@@ -1114,8 +1136,16 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				gs->fc_clk = R.clk;
 			}
 		}
+#ifdef VDL2_CHAIN_FENCE_SC	/* A/B */
 		__threadfence();
 		__syncwarp();
+#else
+		/* release side: every lane's stores are ordered before the barrier, the publishing lane's fence makes them visible
+		   before the progress counter moves (the pattern of a grid-wide barrier) */
+		__syncwarp();
+		if (lane == 0)
+			asm volatile ("fence.acq_rel.gpu;":::"memory");
+#endif
 #ifdef VDL2_CHAIN_STATS	/* debug build: time on the chain (previous tile ready -> this tile published) by kind of tile, ticket[16 + 4 * kind] */
 		if (lane == 0) {
 			asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_t1));
@@ -1123,6 +1153,11 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 			const int kind = idle_at_start ? (trig ? (idle_end ? 3 : 2) : (pre.used ? 0 : 1)) : (idle_end ? (trig ? 6 : 5) : 4);
 			atomicAdd(kp.ticket + 16 + 4 * kind, 1u);
 			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 16 + 4 * kind + 2), cs_t1 - cs_t0);
+			if (kind == 0) {	/* the plain idle step in three parts: state load, demodulator, state store + fence */
+				atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 48), cs_ta - cs_t0);
+				atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 50), cs_tb - cs_ta);
+				atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 52), cs_t1 - cs_tb);
+			}
 		}
 #endif
 		if (lane == 0)
