@@ -832,13 +832,74 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 			nb = nb < 32 ? nb : 32;
 			if (r >= 4)
 				nb = 1;	/* irregular clock (only after a non-finite timing estimate) */
+			const bool grid_ok = bp.valid && r == bp.r && ((ds0 - bp.d0) & 7) == 0;
+			const bool dec_ok = grid_ok && !head && bp.dlast >= bp.d0 + 8 && vw::f2bits(R.df) == vw::f2bits(bp.df)
+			    && !(TAPS && (kp.taps & VDL2_TAP_SYMS_BIT));
+			if (dec_ok && ds0 >= bp.d0 + 8 && ds0 <= bp.dlast) {
+				/* ---- every symbol from here to the end of the tile (or of the burst) was decided ahead of the chain (BurstPre):
+				   what is left is the descrambler and the bytes, one pass with a lane per BYTE of the bit stream
+				   (the R.nbitacc bits left over, then 3 bits per symbol) instead of a batch per 32 symbols ---- */
+				int n = ((bp.dlast - ds0) >> 3) + 1;
+				n = n < remain ? n : remain;
+				const int nbits = R.nbitacc + 3 * n;
+				const int total = g.nd + g.nf;
+				int nbytes = nbits >> 3;
+				if (R.bytes_done + nbytes > total)
+					nbytes = total - R.bytes_done;
+				const unsigned char *hb = vw::as_shared(S.hb) + (ds0 >> 3);
+				unsigned last = 0;	/* byte number nbytes of the stream: the bits left over */
+#pragma unroll 1
+				for (int b0 = 0; b0 <= nbytes; b0 += 32) {
+					const int b = b0 + lane;
+					const int sp = 8 * b - R.nbitacc;	/* symbol bit the byte starts at; it spans at most 4 symbols */
+					const int j0 = sp > 0 ? (sp * 43691) >> 17 : 0;	/* sp / 3 */
+					unsigned h4 = 0;
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const int j = j0 + k;
+						if (j < n && b <= nbytes) {
+							const unsigned ab = hb[j];
+							const int bb = 3 * (R.symidx + j);	/* descrambler bits of the symbol, d8psk.c:54-65 */
+							const unsigned w0 = kp.soft ? vw::ldg(kp.scr + ((bb >> 5) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[(bb >> 5) & (VDL2_SCR_WORDS - 1)];
+							const unsigned w1 = kp.soft ? vw::ldg(kp.scr + (((bb >> 5) + 1) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[((bb >> 5) + 1) & (VDL2_SCR_WORDS - 1)];
+							const unsigned s3 = (unsigned)((((unsigned long long)w1 << 32) | w0) >> (bb & 31)) & 7u;
+							h4 |= ((ab & 7u & ~s3) | ((ab >> 3) & s3)) << (3 * k);
+						}
+					}
+					const unsigned byte = (sp >= 0 ? (h4 >> (sp - 3 * j0)) : ((unsigned)R.bitacc | (h4 << (-sp)))) & 0xffu;
+					if (b < nbytes)
+						curblk[byte_slot(g, R.bytes_done + b)] = (unsigned char)byte;
+					const unsigned lm = vw::ballot(b == nbytes);
+					if (lm)
+						last = vw::shfl(byte, vw::ffs(lm) - 1);
+				}
+				int left = nbits - 8 * nbytes;
+				if (left > 7)
+					left = 0;	/* only at the end of the burst: discarded (d8psk.c:203) */
+				const int dl = ds0 + 8 * (n - 1);
+				R.bitacc = (int)(last & ((1u << left) - 1u));
+				R.nbitacc = left;
+				R.bytes_done += nbytes;
+				R.symidx += n;
+				R.P1 = vw::as_shared(S.pht)[VDL2_BPH(dl)];
+				R.clk = r;
+				pos = dl + 1;
+				if (R.bytes_done >= total) {
+					vw::fence();
+					vw::sync();
+					emit_block(kp, ch, R, dump_base + dl, chn, Fr);	/* decodeVdlm2 hand-off, d8psk.c:201 */
+					R.state = VDL2_ST_WSYNC;
+				}
+				continue;
+			}
+			if (dec_ok && ds0 < bp.d0 + 8) {	/* the symbols in front of the decided ones first, so that the pass above takes all the rest */
+				const int nfirst = (bp.d0 + 8 - ds0) >> 3;
+				nb = nb < nfirst ? nb : nfirst;
+			}
 			const int d = ds0 + 8 * lane;
 			float Pn = 0.f;
-			bool have6;	/* this lane's symbol was decided ahead of the chain (BurstPre) */
 			{
-				const bool grid_ok = bp.valid && r == bp.r && ((ds0 - bp.d0) & 7) == 0;
-				const bool have = grid_ok && d >= bp.d0 && d <= bp.dlast;
-				have6 = have && !head && d >= bp.d0 + 8 && vw::f2bits(R.df) == vw::f2bits(bp.df) && !(TAPS && (kp.taps & VDL2_TAP_SYMS_BIT));
+				const bool have = grid_ok && d >= bp.d0 && d <= bp.dlast;	/* phase computed ahead of the chain (BurstPre) */
 				if (have)
 					Pn = vw::as_shared(S.pht)[VDL2_BPH(d)];
 				else if (lane < nb)
@@ -852,11 +913,7 @@ template < bool TAPS > VQ void demod_tile(const Vdl2KParams & kp, int ch, int ch
 			const int si = R.symidx + lane;
 			float D = 0.f, v[3] = { 0.f, 0.f, 0.f };
 			int gi = 128;
-			unsigned ab;
-			if (have6)
-				ab = vw::as_shared(S.hb)[d >> 3];
-			else
-				ab = sym_decide(kp, Pn, Pp, R.df, D, gi, v);
+			const unsigned ab = sym_decide(kp, Pn, Pp, R.df, D, gi, v);
 			/* descrambler, d8psk.c:54-65: bits 3 si .. 3 si + 2 of the sequence */
 			const int b0 = 3 * si;
 			const unsigned w0 = kp.soft ? vw::ldg(kp.scr + ((b0 >> 5) & (VDL2_SCR_WORDS - 1))) : c_tab.scr[(b0 >> 5) & (VDL2_SCR_WORDS - 1)];
