@@ -8,6 +8,7 @@
 #ifndef VDL2_COMMON_H
 #define VDL2_COMMON_H
 #include <stdint.h>
+#include <stddef.h>
 #include <vector_types.h>
 
 #define VDL2_DUMPS_PER_ROW 84
@@ -53,11 +54,12 @@ struct Vdl2ChanState {
 	/* forecast for the speculative idle search of later tiles: as far as is known the channel is idle from global dump
 	   fc_dump on, with tick clock fc_clk there.  Written at the end of an idle tile and, early, as soon as the header
 	   of a burst gives its length; read without synchronisation (a wrong guess is detected, see idle_run) */
+	int32_t pad[2];		/* the forecast below is 16-byte aligned: a waiting tile polls it with ONE vector load */
 	int64_t fc_dump;
 	int32_t fc_clk;
 	float fc_df;		/* frequency offset of the burst that ends at fc_dump (BurstPre) */
-	int32_t pad[2];
 };
+static_assert(offsetof(Vdl2ChanState, fc_dump) % 16 == 0 && sizeof(Vdl2ChanState) % 16 == 0, "forecast: one aligned 16-byte load");
 
 /* constant tables of the kernel (independent of rate and format, so handles can share them) */
 struct Vdl2Tables {

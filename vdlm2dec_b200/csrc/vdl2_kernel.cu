@@ -122,18 +122,27 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
      0..7   the channel is idle there: the tick clock the tile begins with (speculative pass A, see IdlePre);
      8..39  the tile starts inside that burst: 8 + 4 * (first symbol dump mod 8) + tap phase (burst phases ahead, see BurstPre);
      -1     nothing.
-   Two unsynchronised words: a torn pair gives a wrong key, and the demodulator verifies whatever was precomputed under it. */
-static __device__ __forceinline__ int forecast_key(const Vdl2ChanState * gs, long long dump_base, int nd, int &bd0, int &bdlast, float &bdf)
+   Read without synchronisation (one 16-byte load, written as three words): a torn or stale forecast gives a wrong key, and the
+   demodulator verifies whatever was precomputed under it. */
+/* the forecast as one aligned 16-byte volatile load: (fc_dump lo, fc_dump hi, fc_clk, fc_df) */
+static __device__ __forceinline__ uint4 forecast_load(const Vdl2ChanState * gs)
 {
-	const long long F = *(const volatile long long *)&gs->fc_dump;
-	const int c = *(const volatile int *)&gs->fc_clk & 7;
+	uint4 v;
+	asm volatile ("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];":"=r" (v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w):"l"(&gs->fc_dump));
+	return v;
+}
+
+static __device__ __forceinline__ int forecast_key(const uint4 fc, long long dump_base, int nd, int &bd0, int &bdlast, float &bdf)
+{
+	const long long F = (long long)(((unsigned long long)fc.y << 32) | fc.x);
+	const int c = (int)fc.z & 7;
 	if (F > dump_base) {	/* the last symbol of the burst is at dump F - 1, one symbol every 8 dumps */
 		const long long rel = F - 1 - dump_base;
 		if (c >= 4 || rel < 24)
 			return -1;
 		bd0 = (int)(rel & 7);
 		bdlast = rel < (long long)nd ? (int)rel : nd - 1;
-		bdf = *(const volatile float *)&gs->fc_df;
+		bdf = __uint_as_float(fc.w);
 		return 8 + 4 * bd0 + c;
 	}
 	if (dump_base - F > (long long)VDL2_SPEC_AHEAD * VDL2_TILE_DUMPS)
@@ -995,7 +1004,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				bp.valid = 0;
 				pre.valid = 0;
 				pre.pos0 = 0;
-				guess = forecast_key(gs, dump_base, nd, bd0, bdlast, bdf);
+				guess = forecast_key(forecast_load(gs), dump_base, nd, bd0, bdlast, bdf);
 				if (guess < 0)
 					continue;
 				if (guess >= 8) {	/* as far as is known the tile starts inside a burst */
@@ -1017,11 +1026,16 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				int redo = 0;
 				if (lane == 0) {
 					const volatile int *pr = kp.progress + ch;
-					while ((int)((unsigned)(kp.tile_base + tile) - (unsigned)*pr) > 0) {	/* tiles completed since create (wrap-safe): launches may overlap */
+					for (;;) {
+						/* progress and forecast in flight together: one L2 round trip per poll, not two */
+						const unsigned done = (unsigned)*pr;
+						const uint4 fc = forecast_load(gs);
+						if ((int)((unsigned)(kp.tile_base + tile) - done) <= 0)	/* tiles completed since create (wrap-safe): launches may overlap */
+							break;
 						if (can_spec && nrespec < VDL2_MAX_RESPEC) {
 							int t0, t1;
 							float t2;
-							const int g2 = forecast_key(gs, dump_base, nd, t0, t1, t2);
+							const int g2 = forecast_key(fc, dump_base, nd, t0, t1, t2);
 							if (g2 >= 0 && g2 != guess) {
 								redo = 1;
 								break;
@@ -1071,7 +1085,9 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				R.n_steps = __ldcg(&gs->n_steps);
 				R.n_syncs = __ldcg(&gs->n_syncs);
 				R.n_syms = __ldcg(&gs->n_syms);
+#ifdef VDL2_STATE_LOAD_FENCE	/* A/B: round 1 split the state load in two dependent L2 round trips here; __syncwarp below orders the history stores */
 				__threadfence_block();
+#endif
 				n_dumps = __ldcg(&gs->n_dumps);
 				chn = __ldcg(&gs->chn);
 				Fr = __ldcg(&gs->Fr);
