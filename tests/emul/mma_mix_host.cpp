@@ -4,8 +4,8 @@
  *
  * It models exactly what the kernel relies on and nothing else: the 64B-swizzled TMA box layout with zero fill outside
  * the tensor, the stage ring with its W/R schedule bits, ldmatrix.x4 row addressing, the m16n8k32 fragment layouts
- * (checked on a B200 by tools/ubench/imma_ubench.cu), the B masks, the accumulator start values, the FFMA2 / two-shuffle
- * epilogue that leaves every lane with (re, im) of one row.  tests/test_host_logic.py compares its dumps with the oracle's T1 tap, so the index
+ * (checked on a B200 by tools/ubench/imma_ubench.cu), the B masks, the accumulator start values, the FFMA2 epilogue and the
+ * exchange over a quad of dumps that leaves every lane with (re, im) of ONE dump of four rows.  tests/test_host_logic.py compares its dumps with the oracle's T1 tap, so the index
  * arithmetic and the tables are pinned in the CPU tier; the GPU tier pins the kernel itself.
  */
 #include <math.h>
@@ -76,6 +76,9 @@ extern "C" int emul_mma_mix(const uint8_t * rows, int nrows, unsigned fs, unsign
 		E.tma_load(b, b);
 	int st = 0, box = 0;
 	E.stage_waited[0] = true;	/* the wait in front of the loop */
+	static float ppair[2][32][4], va[32][4], keep[32][4];	/* partial sums of a pair of dumps; completed components after round A */
+	if (ND % 4)
+		return -2;	/* whole quads of dumps per row */
 	for (int dk = 0; dk < ND; dk++) {
 		const unsigned sk = sched[dk];
 		const int st1 = (st + 1 == MM_NST) ? 0 : st + 1;
@@ -176,23 +179,39 @@ extern "C" int emul_mma_mix(const uint8_t * rows, int nrows, unsigned fs, unsign
 				p[lane][q] = yx + yy;
 			}
 		}
-		float v[32][2];
-		for (int lane = 0; lane < 32; lane++) {
-			const int t = lane & 3;
-			const bool odd = t & 1;
-			const float r0 = odd ? p[lane ^ 1][2] : p[lane ^ 1][0];	/* what the partner sends: odd ? p[0] : p[2] of the PARTNER */
-			const float r1 = odd ? p[lane ^ 1][3] : p[lane ^ 1][1];
-			const Vdl2MmaI4 dc = dt[dk * 4 + t];
-			const float sf = as_float(dc.z), corr = as_float(dc.w);
-			v[lane][0] = fmaf((odd ? p[lane][2] : p[lane][0]) + r0, sf, corr);
-			v[lane][1] = fmaf((odd ? p[lane][3] : p[lane][1]) + r1, sf, corr);
-		}
-		for (int lane = 0; lane < 32; lane++) {
-			const int g = lane >> 2, t = lane & 3, hi = t >> 1;
-			const float rx = hi ? v[lane ^ 2][1] : v[lane ^ 2][0];	/* the partner sends hi ? v0 : v1 of ITS hi */
-			const int row = g + 16 * (t & 1) + 8 * hi;
-			out[((size_t) row * ND + dk) * 2] = hi ? rx : v[lane][0];
-			out[((size_t) row * ND + dk) * 2 + 1] = hi ? v[lane][1] : rx;
+		/* Exchange over a quad of dumps (the kernel's MM_QUAD_STORE path): the four lanes of a quad (same g) end up with ONE dump each
+		   -- lane t with dump 4q + t -- of the four rows g, g + 8, g + 16, g + 24, so that a store instruction touches 8 rows with one
+		   full 32-byte sector per row instead of 32 rows with half a sector each.
+		   round A, once per pair of dumps (lane ^ 1 holds the other digits of the same component): a lane keeps the dump of the pair
+		   with its own parity and sends its partial sums of the other one;
+		   round B, once per quad (lane ^ 2 holds the other component): t < 2 keeps the first pair's dump, t >= 2 the second pair's. */
+		for (int lane = 0; lane < 32; lane++)
+			for (int q = 0; q < 4; q++)
+				ppair[dk & 1][lane][q] = p[lane][q];
+		if (dk & 1) {
+			for (int lane = 0; lane < 32; lane++) {
+				const int t = lane & 3, odd = t & 1;
+				const Vdl2MmaI4 dc = dt[(dk - 1 + odd) * 4 + t];	/* the kept dump's scale and offset correction */
+				const float sf = as_float(dc.z), corr = as_float(dc.w);
+				for (int j = 0; j < 4; j++) {
+					const float x = ppair[odd][lane ^ 1][j];	/* the partner sends its partial of the dump it does not keep = my parity */
+					va[lane][j] = fmaf(ppair[odd][lane][j] + x, sf, corr);
+				}
+			}
+			if (!(dk & 2)) {
+				memcpy(keep, va, sizeof keep);
+			} else {
+				for (int lane = 0; lane < 32; lane++) {
+					const int g = lane >> 2, t = lane & 3, hi = t >> 1;
+					for (int j = 0; j < 4; j++) {
+						const float x = hi ? va[lane ^ 2][j] : keep[lane ^ 2][j];	/* the partner (other hi) sends hi' ? keep : va */
+						const float mine = hi ? va[lane][j] : keep[lane][j];
+						const int row = g + 8 * j, d = dk - 3 + t;
+						out[((size_t) row * ND + d) * 2] = hi ? x : mine;
+						out[((size_t) row * ND + d) * 2 + 1] = hi ? mine : x;
+					}
+				}
+			}
 		}
 		if (sk & VDL2_MM_R) {
 			if (box + MM_NST < nbox)

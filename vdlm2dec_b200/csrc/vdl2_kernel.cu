@@ -546,6 +546,10 @@ template < int FMT > __device__ __forceinline__ void mix_rows_dp4a(const CUtenso
 #ifndef MM_PREFETCH
 #define MM_PREFETCH 0		/* boxes prefetched into L2 ahead of the stage ring: A/B on B200 (profiles/r2_ab_prefetch.txt): 0 -> 2.69 ms, 8 -> 3.20, 16 -> 3.26, 24 -> 3.34 ms per step: off */
 #endif
+#ifndef MM_QUAD_STORE
+#define MM_QUAD_STORE 1		/* dumps leave the registers a quad of dumps at a time, one dump per lane of a quad (see the exchange in mix_rows_mma): a
+				   store instruction touches 8 rows with a full 32-byte sector each instead of 32 rows with half a sector each.  0: A/B */
+#endif
 #ifndef MM_UNROLL
 #define MM_UNROLL 2		/* dumps per store group: 2 = half a 32-byte sector per lane and store (A/B on B200: 1 % faster than 4, smaller loop) */
 #endif
@@ -634,7 +638,14 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	uint32_t odd = (uint32_t) t & 1u, hi = (uint32_t) t >> 1;
 	/* after the two exchanges below this lane owns (re, im) of ONE row: g + 16 (t & 1) + 8 (t >> 1); four consecutive dumps of it
 	   are one 32-byte sector of the scratch */
+#if MM_QUAD_STORE
+	/* ... or, with the exchange over a quad of dumps, dump 4 q + t of the FOUR rows g, g + 8, g + 16, g + 24 */
+	float2 *dstq = sd + VDL2_HIST + g * VDL2_DUMPS_PER_ROW + t;
+	float keep[4] = { 0.f, 0.f, 0.f, 0.f };	/* first pair of the quad: this lane's component of the dump it keeps, rows g + 8 j */
+	static_assert(MM_UNROLL == 2 && VDL2_DUMPS_PER_ROW % 4 == 0, "the quad exchange runs over two pairs of dumps");
+#else
 	float4 *dst = reinterpret_cast < float4 * >(sd + VDL2_HIST + (g + 16 * (t & 1) + 8 * (t >> 1)) * VDL2_DUMPS_PER_ROW);
+#endif
 	VDL2_PIN(sw16);
 	VDL2_PIN(cwl16);
 	VDL2_PIN(rowoff);
@@ -697,7 +708,11 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 				st = st1;
 			}
 		}
+#if MM_QUAD_STORE
+		float pp[MM_UNROLL][4];	/* [dump of the pair][row g + 8 j]: this lane's digits of its component, weighed and summed */
+#else
 		float2 out[MM_UNROLL];
+#endif
 #pragma unroll
 		for (int u = 0; u < MM_UNROLL; u++) {
 			int c0[4], c1[4];
@@ -721,6 +736,12 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 			const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
 			const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
 			const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;	/* rows g, g + 8, g + 16, g + 24 */
+#if MM_QUAD_STORE
+			pp[u][0] = p0;
+			pp[u][1] = p1;
+			pp[u][2] = p2;
+			pp[u][3] = p3;
+#else
 			/* lane ^ 1 holds the other digits: even lanes complete rows g, g + 8, odd lanes rows g + 16, g + 24 */
 			const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
 			const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
@@ -729,7 +750,41 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 			/* lane ^ 2 holds the other component of the same two rows: t < 2 keeps the first row, t >= 2 the second */
 			const float rx = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 2);
 			out[u] = make_float2(hi ? rx : v0, hi ? v1 : rx);
+#endif
 		}
+#if MM_QUAD_STORE
+		/* Exchange over a quad of dumps 4 q .. 4 q + 3 (two trips through this loop): the four lanes of a quad (same g) hold digits
+		   (lane ^ 1) and components (lane ^ 2) of the same four rows, and end up with ONE dump each -- lane t with dump 4 q + t -- of
+		   all four.  Same number of shuffles as an exchange per dump (3 per dump), same sums in the same order (own + received), but
+		   a store instruction then touches 8 rows with one full sector each instead of 32 rows with half a sector each: the scatter
+		   of the row-per-lane layout was 15 % of all LSU wavefronts of the kernel (ncu, round 2 v19).
+		   round A, per pair: a lane keeps the dump of the pair with its own parity and completes its component of it */
+		{
+			const float sfk = __int_as_float(odd ? dc[1].z : dc[0].z), corrk = __int_as_float(odd ? dc[1].w : dc[0].w);
+			float va[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const float x = __shfl_xor_sync(0xffffffffu, odd ? pp[0][j] : pp[1][j], 1);
+				va[j] = fmaf((odd ? pp[1][j] : pp[0][j]) + x, sfk, corrk);
+			}
+			if (!(dk0 & 2)) {
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					keep[j] = va[j];
+			} else {
+				/* round B, per quad: t < 2 (real parts) keeps the first pair's dump, t >= 2 (imaginary parts) the second pair's */
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const float x = __shfl_xor_sync(0xffffffffu, hi ? keep[j] : va[j], 2);
+					const float mine = hi ? va[j] : keep[j];
+					/* evict-last: the scratch is read back from L2 in phase 2 */
+					asm volatile ("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;"::"l" (dstq + j * 8 * VDL2_DUMPS_PER_ROW), "f"(hi ? x : mine),
+						      "f"(hi ? mine : x), "l"(l2keep):"memory");
+				}
+				dstq += 4;
+			}
+		}
+#else
 		/* MM_UNROLL dumps of this lane's row, contiguous in the time-ordered scratch; evict-last: it is read back from L2 in phase 2 */
 		asm volatile ("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"::"l" (dst), "f"(out[0].x), "f"(out[0].y), "f"(out[1].x), "f"(out[1].y),
 			      "l"(l2keep):"memory");
@@ -738,6 +793,7 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 			      "l"(l2keep):"memory");
 #endif
 		dst += MM_UNROLL / 2;
+#endif
 	}
 }
 
