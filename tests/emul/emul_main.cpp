@@ -211,7 +211,7 @@ extern "C" int emul_demod(const float *dumps, long ndumps, int tile_dumps, int c
 	std::vector < float2 > sd(VDL2_HIST + VDL2_TILE_DUMPS);
 	float hv[32] = { 0 };
 	std::vector < float >pht(VDL2_PHT_LEN, 0.f);
-	std::vector < float2 > vwin(96);
+	std::vector < float2 > vwin(VDL2_BPRE_BUF);	/* 96 for the idle search; burst_prephase stages its windows in vw .. cand0 (contiguous in the kernel) */
 	std::vector < unsigned short >cand(VDL2_CAND_CAP + VDL2_CAND0_CAP);
 	std::vector < float2 > win(VDL2_WIN_LEN);
 	std::vector < unsigned char >hbuf(VDL2_TILE_DUMPS / 8);

@@ -630,15 +630,54 @@ struct BurstPre {
 	float df;		/* and, for all but the first of them, the decisions (sym_decide) under this frequency offset in hb[d >> 3] */
 };
 #define VDL2_BPH(d) (VDL2_PHT_LEN - 1 - ((d) >> 3))
+#define VDL2_BPRE_NS 28		/* symbols per staging pass of burst_prephase: 8 * 28 + 9 = 233 dumps, swizzled into < 240 of the 248 float2 of scratch */
+#define VDL2_BPRE_BUF ((96 * 8 + VDL2_WIN_LEN * 8 + (VDL2_CAND_CAP + VDL2_CAND0_CAP) * 2) / 8)	/* float2 from IdleScratch.vw to the end of cand0 */
+static_assert(((8 * VDL2_BPRE_NS + 9 - 1) | 15) < VDL2_BPRE_BUF, "staged burst windows must fit vw .. cand0");
 
 VQ_RARE void burst_prephase(const Vdl2KParams & kp, const float2 * sd, const IdleScratch & S, BurstPre & bp, int d0, int dlast, int r, float df)
 {
 	float *pht = vw::as_shared(S.pht);
 	unsigned char *hb = vw::as_shared(S.hb);
 	const int dmin = (d0 & 7) + 16;
+#ifdef VDL2_BPRE_DIRECT	/* A/B: every lane fetches its own 17-dump window from L2 -- symbols are 8 dumps = 64 bytes apart, so each of the 17
+				   loads of a batch touches 16 lines: 7 % of all LSU wavefronts of the kernel on the bench workload (ncu, round 2 v19) */
 #pragma unroll 1
 	for (int d = dmin + 8 * vw::lane(); d <= dlast; d += 256)
 		pht[VDL2_BPH(d)] = filt_phase_any(sd, d, r);
+#else
+	/* The windows of VDL2_BPRE_NS consecutive symbols are one contiguous run of 8 NS + 9 dumps: staged with coalesced loads in the
+	   idle-search scratch (vw, win, cand, cand0: contiguous, unused until the idle pass that follows), then every lane filters its
+	   symbol from shared memory.  Entry i sits at i ^ ((i >> 4) & 15), which spreads the 64-byte symbol stride over all banks.
+	   Same taps, same order of the sums as filt_phase_any: the phases are bit identical. */
+	{
+		float2 *buf = vw::as_shared(S.vw);
+		const int lane = vw::lane();
+		float m[17];
+#pragma unroll
+		for (int j = 0; j < 17; j++)
+			m[j] = c_tab.mflt[r + 4 * j < 67 ? r + 4 * j : 67];	/* entries 63..67 are zero */
+#pragma unroll 1
+		for (int db = dmin; db <= dlast; db += 8 * VDL2_BPRE_NS) {
+			const int ns = ((dlast - db) >> 3) + 1 < VDL2_BPRE_NS ? ((dlast - db) >> 3) + 1 : VDL2_BPRE_NS;
+			const int len = 8 * ns + 9;
+			vw::sync();
+			for (int i = lane; i < len; i += 32)
+				buf[i ^ ((i >> 4) & 15)] = vw::ldcg(sd + db + i);
+			vw::sync();
+			if (lane < ns) {
+				float sr = 0.f, si = 0.f;
+#pragma unroll
+				for (int j = 0; j < 17; j++) {
+					const int i = 8 * lane + j;
+					const float2 x = buf[i ^ ((i >> 4) & 15)];
+					sr = vw::fma(x.x, m[j], sr);
+					si = vw::fma(x.y, m[j], si);
+				}
+				pht[VDL2_BPH(db + 8 * lane)] = vw::atan2(si, sr);
+			}
+		}
+	}
+#endif
 	vw::sync();
 #pragma unroll 1
 	for (int d = dmin + 8 + 8 * vw::lane(); d <= dlast; d += 256) {

@@ -865,6 +865,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	scr.cand = reinterpret_cast < unsigned short *>(stage0 + VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8);
 	scr.cand0 = scr.cand + VDL2_CAND_CAP;
 	scr.hb = reinterpret_cast < unsigned char *>(scr.cand0 + VDL2_CAND0_CAP);
+	/* burst_prephase stages its windows in vw .. cand0: they must be one contiguous run of VDL2_BPRE_BUF float2 (they are, by the lines above) */
 	static_assert(VDL2_PHT_LEN * 4 + 96 * 8 + VDL2_WIN_LEN * 8 + (VDL2_CAND_CAP + VDL2_CAND0_CAP) * 2 + VDL2_TILE_DUMPS / 8 <= STAGES_BYTES,
 		      "phase 2 scratch must fit the stages");
 	static_assert(NBAR <= 8, "mbarriers live in 64 bytes");
