@@ -885,7 +885,11 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 	const int nbox = kp.nbox;
 	const int nco = kp.nco_pairs;
 	unsigned long long l2pol;	/* the input is read exactly once: evict-first keeps the per-warp scratch L2 resident */
+#ifdef VDL2_IN_EVICT_NORMAL	/* A/B */
+	asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;":"=l" (l2pol));
+#else
 	asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;":"=l" (l2pol));
+#endif
 	unsigned long long l2keep;	/* the per-warp scratch: written in phase 1, read back in phase 2, should never reach DRAM */
 #ifdef VDL2_MM_NOKEEP	/* A/B */
 	asm volatile ("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;":"=l" (l2keep));
@@ -1083,9 +1087,15 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 				int redo = 0;
 				if (lane == 0) {
 					const volatile int *pr = kp.progress + ch;
+					(void)pr;
 					for (;;) {
 						/* progress and forecast in flight together: one L2 round trip per poll, not two */
+#ifdef VDL2_CHAIN_ACQ_FENCE	/* A/B: volatile load here, fence.acq_rel.gpu after the loop (it also waits for this lane's own scratch stores) */
 						const unsigned done = (unsigned)*pr;
+#else
+						unsigned done;	/* acquire side of the hand-over: the shuffle below extends it to the other lanes */
+						asm volatile ("ld.acquire.gpu.global.u32 %0, [%1];":"=r" (done):"l"(kp.progress + ch):"memory");
+#endif
 						const uint4 fc = forecast_load(gs);
 						if ((int)((unsigned)(kp.tile_base + tile) - done) <= 0)	/* tiles completed since create (wrap-safe): launches may overlap */
 							break;
@@ -1100,7 +1110,7 @@ vdl2_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 						}
 						__nanosleep(VDL2_CHAIN_POLL_NS);
 					}
-#ifndef VDL2_CHAIN_FENCE_SC
+#if !defined(VDL2_CHAIN_FENCE_SC) && defined(VDL2_CHAIN_ACQ_FENCE)
 					/* acquire side of the hand-over: one fence in the polling lane, the warp shuffle below extends it to the others
 					   (a sequentially consistent fence in every lane, __threadfence(), costs a microsecond per tile of the chain) */
 					asm volatile ("fence.acq_rel.gpu;":::"memory");
