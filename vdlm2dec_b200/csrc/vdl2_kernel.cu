@@ -664,7 +664,11 @@ template < int FMT > __device__ __forceinline__ void mix_rows_mma(const CUtensor
 	mbar_wait(smem_u32(bars), phases & 1u);
 	phases ^= 1u;
 	static_assert(VDL2_DUMPS_PER_ROW % MM_UNROLL == 0 && MM_NST >= 4, "whole store groups per row; the phase-2 scratch needs four stages of room");
-#pragma unroll 1
+#ifndef MM_PAIR_UNROLL
+#define MM_PAIR_UNROLL 1	/* A/B: 2 = both pairs of a quad in one loop body (no copies of the kept values, static quad parity; twice the code) */
+#endif
+	constexpr int pair_unroll = MM_PAIR_UNROLL;
+#pragma unroll pair_unroll
 	for (int dk0 = 0; dk0 < VDL2_DUMPS_PER_ROW; dk0 += MM_UNROLL) {
 		/* software pipeline over the MM_UNROLL dumps of a store group: first every dump's window and weights go to registers
 		   (waits, ldmatrix, B + masks), then the tensor-core products and epilogues run back to back while the loads of the
