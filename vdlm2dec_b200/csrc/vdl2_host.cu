@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -47,6 +48,8 @@ struct vdl2gpu {
 	int nco_entries, wext;
 	int smem, grid, n_sm, ctas_per_sm;
 	cudaStream_t stream;
+	bool l2_manage;		/* this handle switches the device's persisting-L2 limit per path (l2_reserve) */
+	size_t l2_want;		/* set-aside of the fused kernel: scratch + mixer tables + 2 MB, capped by the device */
 	cudaEvent_t ev0, ev1;
 	bool ev_valid;
 	/* device */
@@ -572,38 +575,23 @@ static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_p
 		const size_t nslots = (size_t) h->nsmid * h->ctas_per_sm;
 		CK(h, cudaMalloc(&h->d_scratch, sizeof(float2) * nslots * (VDL2_HIST + VDL2_TILE_DUMPS)));
 		CK(h, cudaMemset(h->d_scratch, 0, sizeof(float2) * nslots * (VDL2_HIST + VDL2_TILE_DUMPS)));
-		/* L2 set-aside for what the kernel keeps on chip: the per-warp scratch (written in phase 1, read back in phase 2) and the
-		   per-channel mixer tables carry evict_last hints, but without a reserved share of L2 the 8.6 GB input stream still pushed
+		/* L2 set-aside for what the fused kernel keeps on chip: the per-warp scratch (written in phase 1, read back in phase 2) and
+		   the per-channel mixer tables carry evict_last hints, but without a reserved share of L2 the 8.6 GB input stream still pushed
 		   0.3-0.45 GB of scratch per step out to DRAM (ncu, profiles/r2_ab_l2persist.txt: write-backs 0.3 -> 0.02 GB with the
-		   set-aside, noise probe 2.5 % faster).  The limit belongs to the device context, not to this handle: VDL2_L2_PERSIST_MB=0
-		   leaves it alone, =<n> forces n MB.  The scratch is also marked persisting for accesses without a hint of their own. */
+		   set-aside, noise probe 2.5 % faster).  The limit belongs to the device context, not to this handle, and the one-pass
+		   channeliser (row f3), which keeps nothing on chip, runs 2.2 x SLOWER with half of L2 reserved: so the limit is switched
+		   per path (l2_reserve below: a device call only when the path changes).  VDL2_L2_PERSIST_MB=0 never touches the
+		   limit, =<n> asks for n MB. */
 		const size_t bytes = sizeof(float2) * nslots * (VDL2_HIST + VDL2_TILE_DUMPS);
 		const char *pe = getenv("VDL2_L2_PERSIST_MB");
-		size_t want = bytes + (h->dp4a ? (size_t) nch * (h->dp4a == 2 ? VDL2_MM_BT_ENTRIES * 16 + VDL2_MM_DT_ENTRIES * 16 : 0) : 0) + ((size_t) 2 << 20);
+		size_t want = bytes + (h->dp4a == 2 ? (size_t) nch * (VDL2_MM_BT_ENTRIES * 16 + VDL2_MM_DT_ENTRIES * 16) : 0) + ((size_t) 2 << 20);
 		if (pe)
 			want = (size_t) atoi(pe) << 20;
-		if (want > 0) {
-			cudaDeviceProp prop;
-			CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
-			size_t cur = 0;
-			CK(h, cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize));
-			want = std::min(want, (size_t) prop.persistingL2CacheMaxSize);
-			if (want > cur)	/* never shrink what another handle (or the application) asked for */
-				CK(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-			if (prop.accessPolicyMaxWindowSize > 0) {
-				cudaStreamAttrValue av;
-				memset(&av, 0, sizeof av);
-				av.accessPolicyWindow.base_ptr = h->d_scratch;
-				av.accessPolicyWindow.num_bytes = std::min(bytes, (size_t) prop.accessPolicyMaxWindowSize);
-				av.accessPolicyWindow.hitRatio = 1.0f;
-				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-				CK(h, cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-			}
-			if (getenv("VDL2_PRE_STATS"))
-				fprintf(stderr, "vdl2gpu: L2 set-aside %zu MB (device maximum %d MB), scratch %zu MB\n", std::max(want, cur) >> 20,
-					prop.persistingL2CacheMaxSize >> 20, bytes >> 20);
-		}
+		h->l2_manage = !(pe && atoi(pe) == 0);
+		h->l2_want = std::min(want, (size_t) prop.persistingL2CacheMaxSize);
+		if (getenv("VDL2_PRE_STATS"))
+			fprintf(stderr, "vdl2gpu: L2 set-aside %zu MB (device maximum %d MB), scratch %zu MB\n", h->l2_manage ? h->l2_want >> 20 : (size_t) 0,
+				prop.persistingL2CacheMaxSize >> 20, bytes >> 20);
 	}
 	h->outq_cap = cfg->max_blocks > 0 ? (unsigned)cfg->max_blocks : (unsigned)std::max(4096, nch * 8);
 	CK(h, cudaMalloc(&h->d_outq, sizeof(Vdl2BlockRec) * (size_t) h->outq_cap));
@@ -717,6 +705,26 @@ typedef CUresult(*encode_tiled_t) (CUtensorMap *, CUtensorMapDataType, cuuint32_
 				   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 /* demodulate `nrows` complete rows starting at `base` (device), streams `pitch` bytes apart */
+/* persisting-L2 limit of the device as this library last set it (-1: not yet); one entry per device ordinal */
+static std::atomic < long long >g_l2_limit[64];
+static struct L2LimitInit { L2LimitInit() { for (auto & v:g_l2_limit) v.store(-1); } } g_l2_limit_init;
+
+/* the fused kernel wants its scratch and tables reserved in L2, the channeliser wants all of L2: switch the device limit when the
+   path changes (a handful of times in the life of a process; a relaxed load per launch otherwise) */
+static int l2_reserve(vdl2gpu * h, size_t bytes)
+{
+	if (!h->l2_manage || h->cfg.device < 0 || h->cfg.device >= 64)
+		return 0;
+	if (g_l2_limit[h->cfg.device].load(std::memory_order_relaxed) == (long long)bytes)
+		return 0;
+	CK(h, cudaStreamSynchronize(h->stream));
+	CK(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+	if (bytes == 0)
+		CK(h, cudaCtxResetPersistingL2Cache());
+	g_l2_limit[h->cfg.device].store((long long)bytes, std::memory_order_relaxed);
+	return 0;
+}
+
 static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 {
 	if (nrows <= 0)
@@ -824,6 +832,8 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 	const int grid = (int)std::min < long long >(items, h->grid);
 	if (!h->overlap)	/* an event between two kernels would serialise them */
 		CK(h, cudaEventRecord(h->ev0, h->stream));
+	if (l2_reserve(h, h->l2_want))
+		return -1;
 	cudaError_t e = (cudaError_t) vdl2_kernel_launch(h->cfg.format, h->dp4a, &tmap, &kp, grid, h->smem, h->stream, h->overlap && h->last_was_launch && base != (const void *)h->d_stage);
 	if (e != cudaSuccess)
 		return fail(h, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1056,6 +1066,8 @@ extern "C" int vdl2_channelise_device(vdl2gpu_t * h, const void *d_iq, size_t ns
 	const int grid = (int)std::min < long long >(items, (long long)h->n_sm * 16);
 	CK(h, cudaMemsetAsync(h->d_ticket + 11, 0, 4, h->stream));
 	CK(h, cudaEventRecord(h->ev0, h->stream));
+	if (l2_reserve(h, 0))	/* the channeliser keeps nothing on chip and wants all of L2 */
+		return -1;
 	const cudaError_t e = (cudaError_t) vdl2_channelise_launch(h->cfg.format, &tmap, h->nstreams, h->cfg.ch_per_stream, nrows, h->nbox, h->sched_slot, h->d_w8,
 								  h->d_dcorr, d_out, out_pitch, h->d_ticket + 11, grid, h->stream);
 	if (e != cudaSuccess)
