@@ -718,9 +718,14 @@ static int l2_reserve(vdl2gpu * h, size_t bytes)
 	if (g_l2_limit[h->cfg.device].load(std::memory_order_relaxed) == (long long)bytes)
 		return 0;
 	CK(h, cudaStreamSynchronize(h->stream));
-	CK(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
-	if (bytes == 0)
-		CK(h, cudaCtxResetPersistingL2Cache());
+	/* an optimisation only: where the limit cannot be set (e.g. a context that does not own its L2), carry on without it */
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) {
+		(void)cudaGetLastError();
+		h->l2_manage = false;
+		return 0;
+	}
+	if (bytes == 0 && cudaCtxResetPersistingL2Cache() != cudaSuccess)
+		(void)cudaGetLastError();
 	g_l2_limit[h->cfg.device].store((long long)bytes, std::memory_order_relaxed);
 	return 0;
 }
