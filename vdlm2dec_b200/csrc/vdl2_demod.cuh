@@ -724,6 +724,11 @@ template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, 
 		pos = nd;	/* too short to be worth it: no speculation */
 		return;
 	}
+#ifdef VDL2_CHAIN_STATS	/* debug build: the idle step with an accepted speculation in two parts (head again with the real history | exact fits) */
+	unsigned long long cs_a0 = 0, cs_a1 = 0;
+	if (use_pre)
+		asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_a0));
+#endif
 	{
 		/* one call site, three uses:
 		   spec     all batches, no history: candidates only from step VDL2_PRE_SKIP on;
@@ -744,6 +749,9 @@ template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, 
 			ncand0 = nc;
 			ncand = pre.ncand;
 			overflow = pre.overflow || nc > VDL2_CAND0_CAP;
+#ifdef VDL2_CHAIN_STATS
+			asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_a1));
+#endif
 		} else {
 			ncand = nc;
 			overflow = nc > VDL2_CAND_CAP;
@@ -777,6 +785,16 @@ template < bool TAPS > VQ void idle_run(const Vdl2KParams & kp, int ch, int Fr, 
 		}
 	}
 	if (s0 < 0) {		/* nothing below 4.0 anywhere: the whole run is committed */
+#ifdef VDL2_CHAIN_STATS
+		if (use_pre && lane == 0) {
+			unsigned long long cs_a2;
+			asm volatile ("mov.u64 %0, %%globaltimer;":"=l" (cs_a2));
+			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 54), cs_a1 - cs_a0);
+			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 56), cs_a2 - cs_a1);
+			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 58), (unsigned long long)(ncand0 + ncand));
+			atomicAdd(reinterpret_cast < unsigned long long *>(kp.ticket + 60), 1ull);
+		}
+#endif
 		nph += N;
 		R.p2err = eN2;
 		R.perr = eN1;

@@ -829,6 +829,12 @@ static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 			fprintf(stderr, "vdl2gpu: chain idle step = load %.2f + demodulate %.2f + store/fence %.2f us\n", part[0] * 1e-3 / cs[0], part[1] * 1e-3 / cs[0],
 				part[2] * 1e-3 / cs[0]);
 			cudaMemset(h->d_ticket + 48, 0, sizeof part);
+			unsigned long long sub[4];	/* of "demodulate": head of the tile again with the real history | exact fit of the candidates | candidates | tiles */
+			cudaMemcpy(sub, h->d_ticket + 54, sizeof sub, cudaMemcpyDeviceToHost);
+			if (sub[3])
+				fprintf(stderr, "vdl2gpu: chain idle step, demodulate = head %.2f + exact fits %.2f us (%.1f candidates per tile)\n", sub[0] * 1e-3 / sub[3],
+					sub[1] * 1e-3 / sub[3], (double)sub[2] / sub[3]);
+			cudaMemset(h->d_ticket + 54, 0, sizeof sub);
 		}
 		cudaMemset(h->d_ticket + 16, 0, sizeof cs);
 	}
