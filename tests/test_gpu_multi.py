@@ -110,8 +110,8 @@ def test_multi_shared_streams_and_ragged_split():
     assert len(want) >= nstreams * cps and want.tobytes() == got.tobytes()
 
 
-@pytest.mark.parametrize("fmt", ["cu8", "cs8"])
-def test_channeliser_one_pass_equals_fused_kernel_and_oracle(fmt):
+@pytest.mark.parametrize("fmt,cps", [("cu8", 8), ("cs8", 8), ("cu8", 1), ("cs8", 1)])
+def test_channeliser_one_pass_equals_fused_kernel_and_oracle(fmt, cps):
     """Row f3 (vdl2_channelise_device): ONE pass over each shared stream yields the decimated streams of all its channels.
     They must equal the fused kernel's own T1 tap bit for bit (same integer sums) and the oracle's dumps within the T1 bar;
     3 streams x 8 channels, 70 rows (a ragged last tile)."""
@@ -120,9 +120,9 @@ def test_channeliser_one_pass_equals_fused_kernel_and_oracle(fmt):
     from tests.parity_util import oracle
     from vdlm2dec_b200 import synth
     from vdlm2dec_b200.api import TAP_DUMPS
-    cps, nstreams, rows = 8, 3, 70
+    nstreams, rows = 3, 70          # cps = 1: the kernel's quad-of-dumps store path (one channel per stream)
     n = rows * 2000
-    fos = [-450_000, -325_000, -200_000, -75_000, 50_000, 175_000, 300_000, 425_000]
+    fos = [-450_000, -325_000, -200_000, -75_000, 50_000, 175_000, 300_000, 425_000][:cps] if cps > 1 else [175_000]
     rng = np.random.default_rng(8)
     iq = []
     for s in range(nstreams):

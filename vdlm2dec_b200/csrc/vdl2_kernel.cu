@@ -1310,6 +1310,11 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 	const int t32 = 32 * t;
 	const bool odd = (t & 1) != 0, hi = (t >> 1) != 0;
 	const int rowl = g + 16 * (t & 1) + 8 * (t >> 1);	/* the row this lane owns after the two exchanges */
+#ifdef VDL2_CHANL_NOQUAD	/* A/B */
+	const bool quad = false;
+#else
+	const bool quad = (cp.cps == 1);
+#endif
 	uint32_t phases = 0;
 	const int nitems = cp.ntiles * cp.nstreams;
 	for (;;) {
@@ -1330,6 +1335,7 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 				tma_load_3d(smem_u32(stage0 + b * MM_STAGE), &tmap, bar, b * 32, row0, stream, l2pol);
 			}
 		int st = 0, box = 0;
+		float keep[4] = { 0.f, 0.f, 0.f, 0.f };	/* quad exchange (one channel per stream): first pair's kept values */
 		uint4 Bn[2];
 		int4 dcn[2];
 #pragma unroll
@@ -1397,6 +1403,7 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 					}
 				}
 				float2 o[2];
+				float pp[2][4];
 #pragma unroll
 				for (int u = 0; u < 2; u++) {
 					const unsigned sk = skv[u];
@@ -1416,16 +1423,49 @@ template < int FMT > __global__ void __launch_bounds__(32, 16) vdl2_channelise_k
 					const float2 y2 = ffma2(make_float2(__int_as_float(c1[0]), __int_as_float(c1[1])), sc, nsc);
 					const float2 y3 = ffma2(make_float2(__int_as_float(c1[2]), __int_as_float(c1[3])), sc, nsc);
 					const float p0 = y0.x + y0.y, p1 = y1.x + y1.y, p2 = y2.x + y2.y, p3 = y3.x + y3.y;
-					const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
-					const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
-					const float sf = __int_as_float(dc.z), corr = __int_as_float(dc.w);
-					const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
-					const float rx = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 2);
-					o[u] = make_float2(hi ? rx : v0, hi ? v1 : rx);
+					pp[u][0] = p0;
+					pp[u][1] = p1;
+					pp[u][2] = p2;
+					pp[u][3] = p3;
+					if (!quad) {
+						const float r0 = __shfl_xor_sync(0xffffffffu, odd ? p0 : p2, 1);
+						const float r1 = __shfl_xor_sync(0xffffffffu, odd ? p1 : p3, 1);
+						const float sf = __int_as_float(dc.z), corr = __int_as_float(dc.w);
+						const float v0 = fmaf((odd ? p2 : p0) + r0, sf, corr), v1 = fmaf((odd ? p3 : p1) + r1, sf, corr);
+						const float rx = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 2);
+						o[u] = make_float2(hi ? rx : v0, hi ? v1 : rx);
+					}
 				}
-				if (rowok)
-					__stcs(reinterpret_cast < float4 * >(cp.out + (size_t) ch * cp.out_pitch + (size_t) (row0 + rowl) * VDL2_DUMPS_PER_ROW + dk0),
-					       make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+				if (!quad) {
+					if (rowok)
+						__stcs(reinterpret_cast < float4 * >(cp.out + (size_t) ch * cp.out_pitch + (size_t) (row0 + rowl) * VDL2_DUMPS_PER_ROW + dk0),
+						       make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+				} else {
+					/* one channel per stream: the exchange over a quad of dumps of the fused mixer (mix_rows_mma) -- lane t ends up with
+					   dump 4 q + t of the rows g, g + 8, g + 16, g + 24, so a store touches 8 rows with a full sector each.  Same sums in
+					   the same order: the values stay bit identical to the fused kernel's */
+					const float sfk = __int_as_float(odd ? dcc[1].z : dcc[0].z), corrk = __int_as_float(odd ? dcc[1].w : dcc[0].w);
+					float va[4];
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						const float x = __shfl_xor_sync(0xffffffffu, odd ? pp[0][j] : pp[1][j], 1);
+						va[j] = fmaf((odd ? pp[1][j] : pp[0][j]) + x, sfk, corrk);
+					}
+					if (!(dk0 & 2)) {
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+							keep[j] = va[j];
+					} else {
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							const float x = __shfl_xor_sync(0xffffffffu, hi ? keep[j] : va[j], 2);
+							const float mine = hi ? va[j] : keep[j];
+							if (row0 + g + 8 * j < cp.nrows)
+								__stcs(cp.out + (size_t) ch * cp.out_pitch + (size_t) (row0 + g + 8 * j) * VDL2_DUMPS_PER_ROW + (dk0 - 2) + t,
+								       make_float2(hi ? x : mine, hi ? mine : x));
+						}
+					}
+				}
 			}
 			__syncwarp();
 #pragma unroll
