@@ -49,6 +49,7 @@ struct vdl2gpu {
 	int smem, grid, n_sm, ctas_per_sm;
 	cudaStream_t stream;
 	bool l2_manage;		/* this handle switches the device's persisting-L2 limit per path (l2_reserve) */
+	bool l2_counted;	/* ... and is counted in g_l2_users */
 	size_t l2_want;		/* set-aside of the fused kernel: scratch + mixer tables + 2 MB, capped by the device */
 	cudaEvent_t ev0, ev1;
 	bool ev_valid;
@@ -135,6 +136,33 @@ static int fail(vdl2gpu * h, const char *fmt, ...)
 }
 
 #define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+/* persisting-L2 limit of the device as this library last set it (-1: not yet); one entry per device ordinal */
+static std::atomic < long long >g_l2_limit[64];
+static std::atomic < int >g_l2_users[64];	/* live handles per device that manage the limit: the last one out puts it back to 0 */
+static struct L2LimitInit { L2LimitInit() { for (auto & v:g_l2_limit) v.store(-1); } } g_l2_limit_init;
+
+/* the fused kernel wants its scratch and tables reserved in L2, the channeliser wants all of L2: switch the device limit when the
+   path changes (a handful of times in the life of a process; a relaxed load per launch otherwise) */
+static int l2_reserve(vdl2gpu * h, size_t bytes)
+{
+	if (!h->l2_manage || h->cfg.device < 0 || h->cfg.device >= 64)
+		return 0;
+	if (g_l2_limit[h->cfg.device].load(std::memory_order_relaxed) == (long long)bytes)
+		return 0;
+	CK(h, cudaStreamSynchronize(h->stream));
+	/* an optimisation only: where the limit cannot be set (e.g. a context that does not own its L2), carry on without it */
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) {
+		(void)cudaGetLastError();
+		h->l2_manage = false;
+		return 0;
+	}
+	if (bytes == 0 && cudaCtxResetPersistingL2Cache() != cudaSuccess)
+		(void)cudaGetLastError();
+	g_l2_limit[h->cfg.device].store((long long)bytes, std::memory_order_relaxed);
+	return 0;
+}
+
 
 extern "C" int vdl2_abi_version(void)
 {
@@ -588,6 +616,10 @@ static int create_body(vdl2gpu * h, const vdl2_config_t * cfg, const vdl2_chan_p
 		if (pe)
 			want = (size_t) atoi(pe) << 20;
 		h->l2_manage = !(pe && atoi(pe) == 0);
+		if (h->l2_manage && cfg->device >= 0 && cfg->device < 64) {
+			g_l2_users[cfg->device].fetch_add(1);
+			h->l2_counted = true;
+		}
 		h->l2_want = std::min(want, (size_t) prop.persistingL2CacheMaxSize);
 		if (getenv("VDL2_PRE_STATS"))
 			fprintf(stderr, "vdl2gpu: L2 set-aside %zu MB (device maximum %d MB), scratch %zu MB\n", h->l2_manage ? h->l2_want >> 20 : (size_t) 0,
@@ -639,6 +671,8 @@ extern "C" int vdl2_destroy(vdl2gpu_t * h)
 	cudaSetDevice(h->cfg.device);
 	if (h->stream)
 		cudaStreamSynchronize(h->stream);
+	if (h->l2_counted && h->cfg.device >= 0 && h->cfg.device < 64 && g_l2_users[h->cfg.device].fetch_sub(1) == 1 && h->stream)
+		(void)l2_reserve(h, 0);	/* the device limit goes back to what a fresh context has */
 	cudaFree(h->d_state);
 	cudaFree(h->d_wtab);
 	cudaFree(h->d_dcorr);
@@ -705,31 +739,6 @@ typedef CUresult(*encode_tiled_t) (CUtensorMap *, CUtensorMapDataType, cuuint32_
 				   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 /* demodulate `nrows` complete rows starting at `base` (device), streams `pitch` bytes apart */
-/* persisting-L2 limit of the device as this library last set it (-1: not yet); one entry per device ordinal */
-static std::atomic < long long >g_l2_limit[64];
-static struct L2LimitInit { L2LimitInit() { for (auto & v:g_l2_limit) v.store(-1); } } g_l2_limit_init;
-
-/* the fused kernel wants its scratch and tables reserved in L2, the channeliser wants all of L2: switch the device limit when the
-   path changes (a handful of times in the life of a process; a relaxed load per launch otherwise) */
-static int l2_reserve(vdl2gpu * h, size_t bytes)
-{
-	if (!h->l2_manage || h->cfg.device < 0 || h->cfg.device >= 64)
-		return 0;
-	if (g_l2_limit[h->cfg.device].load(std::memory_order_relaxed) == (long long)bytes)
-		return 0;
-	CK(h, cudaStreamSynchronize(h->stream));
-	/* an optimisation only: where the limit cannot be set (e.g. a context that does not own its L2), carry on without it */
-	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) {
-		(void)cudaGetLastError();
-		h->l2_manage = false;
-		return 0;
-	}
-	if (bytes == 0 && cudaCtxResetPersistingL2Cache() != cudaSuccess)
-		(void)cudaGetLastError();
-	g_l2_limit[h->cfg.device].store((long long)bytes, std::memory_order_relaxed);
-	return 0;
-}
-
 static int run_rows(vdl2gpu * h, const void *base, size_t pitch, int nrows)
 {
 	if (nrows <= 0)
